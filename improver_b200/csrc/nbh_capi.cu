@@ -1,0 +1,112 @@
+// C ABI of libimprover_b200.so (declared in include/improver_b200.h).
+#include <stdarg.h>
+
+#include <cmath>
+
+#include "nbh_common.cuh"
+
+namespace nbh {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// Host preparation of one threshold, mirroring the dtype handling of
+// improver/threshold.py:434 (threshold cast to the float32 data dtype) and
+// numpy's weak-scalar promotion of the python-float fuzzy bounds.
+int make_thr_dev(const NbhThreshold& h, ThrDev* d) {
+  memset(d, 0, sizeof(*d));
+  NBH_REQUIRE(h.op >= NBH_OP_GT && h.op <= NBH_OP_LE, "unknown comparison operator code %d", h.op);
+  d->op = h.op;
+  d->thr = (float)h.value;
+  if (h.lo == h.hi) {           // threshold.py:438-439
+    d->mode = 1;
+    return 0;
+  }
+  NBH_REQUIRE(h.lo <= h.value && h.value <= h.hi, "Threshold must be within bounds: !( %g <= %g <= %g )",
+              h.lo, h.value, h.hi);
+  d->mode = 2;
+  d->lo = (float)h.lo;
+  const float hi = (float)h.hi;
+  d->den_lo = d->thr - d->lo;
+  d->den_hi = hi - d->thr;
+  // rescale() raises on a zero input range (rescale.py:50-53)
+  NBH_REQUIRE(d->den_lo != 0.f && d->den_hi != 0.f,
+              "Cannot rescale a zero input range (fuzzy bound equals the threshold in float32)");
+  d->rcp_lo = (float)(1.0 / (double)d->den_lo);
+  d->rcp_hi = (float)(1.0 / (double)d->den_hi);
+  return 0;
+}
+
+int run_square(const NbhDesc*, const float*, float*, uint8_t*, int32_t*, void*, size_t, cudaStream_t);
+size_t square_workspace_bytes(const NbhDesc&);
+int validate_desc(const NbhDesc*);
+int run_circular(const NbhDesc*, const float*, float*, uint8_t*, int32_t*, void*, size_t, cudaStream_t);
+size_t circular_workspace_bytes(const NbhDesc&);
+int run_percentiles(const float*, float*, const float*, int, long long, int, int, int, int32_t*, void*,
+                    size_t, cudaStream_t);
+size_t percentiles_workspace_bytes(long long, int, int, int);
+int run_threshold(const float*, const uint8_t*, float*, int32_t*, const NbhThreshold*, int, long long,
+                  long long, int32_t*, cudaStream_t);
+
+}  // namespace nbh
+
+extern "C" {
+
+int nbh_version(void) { return NBH_ABI_VERSION; }
+
+const char* nbh_last_error(void) { return nbh::g_err; }
+
+int nbh_device_info(int32_t* sm_count, int64_t* smem_optin_bytes) {
+  int dev = 0, n = 0, s = 0;
+  NBH_CHECK_CUDA(cudaGetDevice(&dev));
+  NBH_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  NBH_CHECK_CUDA(cudaDeviceGetAttribute(&s, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (sm_count) *sm_count = n;
+  if (smem_optin_bytes) *smem_optin_bytes = s;
+  return 0;
+}
+
+size_t nbh_workspace_bytes(const NbhDesc* desc) {
+  if (!desc) return 0;
+  size_t a = nbh::square_workspace_bytes(*desc);
+  size_t b = nbh::circular_workspace_bytes(*desc);
+  return a > b ? a : b;
+}
+
+int nbh_square_f32(const NbhDesc* desc, const float* in, float* out, uint8_t* out_mask, int32_t* status,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  return nbh::run_square(desc, in, out, out_mask, status, workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int nbh_circular_f32(const NbhDesc* desc, const float* in, float* out, uint8_t* out_mask, int32_t* status,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  return nbh::run_circular(desc, in, out, out_mask, status, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int nbh_percentiles_f32(const float* in, float* out, const float* pct, int32_t n_pct, int64_t n_slices,
+                        int32_t ny, int32_t nx, int32_t cells, int32_t* status, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  return nbh::run_percentiles(in, out, pct, n_pct, n_slices, ny, nx, cells, status, workspace,
+                              workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+size_t nbh_percentiles_workspace_bytes(int64_t n_slices, int32_t ny, int32_t nx, int32_t cells) {
+  return nbh::percentiles_workspace_bytes(n_slices, ny, nx, cells);
+}
+
+int nbh_threshold_f32(const float* in, const uint8_t* mask_nd, float* out, int32_t* contrib,
+                      const NbhThreshold* thresholds, int32_t n_thresholds, int64_t n_collapse,
+                      int64_t n_points, int32_t* status, void* stream) {
+  return nbh::run_threshold(in, mask_nd, out, contrib, thresholds, n_thresholds, n_collapse, n_points,
+                            status, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+// Shared device/host helpers for the improver_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/improver_b200.h"
+
+namespace nbh {
+
+void set_error(const char* fmt, ...);
+
+#define NBH_CHECK_CUDA(expr)                                                         \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      nbh::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                     __LINE__);                                                      \
+      return 2;                                                                      \
+    }                                                                                \
+  } while (0)
+
+#define NBH_REQUIRE(cond, ...)       \
+  do {                               \
+    if (!(cond)) {                   \
+      nbh::set_error(__VA_ARGS__);   \
+      return 1;                      \
+    }                                \
+  } while (0)
+
+constexpr int kMaxThresholds = 8;   // thresholds evaluated per launch group
+
+// Device-side description of one threshold.  All float32 so that the truth
+// value follows numpy's float32 arithmetic at improver/threshold.py:441-455 /
+// improver/utilities/rescale.py:63-65 operation by operation.
+struct ThrDev {
+  float thr;      // float32(threshold)                       threshold.py:434
+  float lo;       // float32(bounds[0])   subtracted below thr
+  float den_lo;   // thr - lo             (float32 subtraction)
+  float rcp_lo;   // RN(1 / den_lo)       for the exact division sequence
+  float den_hi;   // float32(bounds[1]) - thr
+  float rcp_hi;
+  int mode;       // 0 raw data, 1 deterministic compare, 2 fuzzy
+  int op;         // NBH_OP_*
+};
+
+struct ThrSet {
+  ThrDev t[kMaxThresholds];
+  int n;          // 0 => raw
+};
+
+int make_thr_dev(const NbhThreshold& h, ThrDev* d);
+
+// Correctly rounded a / den for 0 <= a <= den, den normal, using the host
+// rounded reciprocal (Markstein: q0 = a*r; rem = a - den*q0 exact via FMA;
+// q = q0 + rem*r).  Matches numpy's IEEE float32 division; checked against the
+// oracle bit for bit in tests/test_gpu_threshold.py.
+__device__ __forceinline__ float div_exact(float a, float den, float rcp) {
+  float q0 = __fmul_rn(a, rcp);
+  float rem = __fmaf_rn(-den, q0, a);
+  return __fmaf_rn(rem, rcp, q0);
+}
+
+// Threshold._calculate_truth_value for one unmasked value (threshold.py:407-471).
+__device__ __forceinline__ float truth_value(float d, const ThrDev& p) {
+  if (p.mode == 0) return d;
+  if (p.mode == 1) {
+    bool b;
+    switch (p.op) {
+      case NBH_OP_GT: b = d > p.thr; break;
+      case NBH_OP_GE: b = d >= p.thr; break;
+      case NBH_OP_LT: b = d < p.thr; break;
+      default: b = d <= p.thr; break;
+    }
+    return b ? 1.0f : 0.0f;
+  }
+  // fuzzy: where(d < thr, clip((d-lo)*0.5/(thr-lo) + 0, 0, .5),
+  //                        clip((d-thr)*0.5/(hi-thr) + .5, .5, 1))
+  const bool below = d < p.thr;
+  const float base = below ? p.lo : p.thr;
+  const float den = below ? p.den_lo : p.den_hi;
+  const float rcp = below ? p.rcp_lo : p.rcp_hi;
+  const float off = below ? 0.0f : 0.5f;
+  float a = __fsub_rn(d, base);
+  // clamping the numerator to [0, den] is equivalent to the reference's clip
+  // of the quotient (division by den > 0 and *0.5 are monotone) and keeps
+  // +-inf inputs finite.
+  a = fminf(fmaxf(a, 0.0f), den);
+  float ah = __fmul_rn(a, 0.5f);
+  float v = __fadd_rn(div_exact(ah, den, rcp), off);
+  if (p.op >= NBH_OP_LT) v = __fsub_rn(1.0f, v);     // threshold.py:468-469
+  return v;
+}
+
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+template <int VEC> struct VecLoad;
+template <> struct VecLoad<1> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = __ldg(p); }
+  static __device__ __forceinline__ void st(float* p, const float* v) { p[0] = v[0]; }
+  static __device__ __forceinline__ void ldm(const uint8_t* p, uint8_t* m) { m[0] = __ldg(p); }
+};
+template <> struct VecLoad<2> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = t.x; v[1] = t.y;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  }
+  static __device__ __forceinline__ void ldm(const uint8_t* p, uint8_t* m) {
+    uchar2 t = __ldg(reinterpret_cast<const uchar2*>(p));
+    m[0] = t.x; m[1] = t.y;
+  }
+};
+template <> struct VecLoad<4> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  static __device__ __forceinline__ void ldm(const uint8_t* p, uint8_t* m) {
+    uchar4 t = __ldg(reinterpret_cast<const uchar4*>(p));
+    m[0] = t.x; m[1] = t.y; m[2] = t.z; m[3] = t.w;
+  }
+};
+
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace nbh

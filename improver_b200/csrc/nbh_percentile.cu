@@ -1,0 +1,236 @@
+// Neighbourhood percentiles: replaces the hot loop of
+// GeneratePercentilesFromANeighbourhood.pad_and_unpad_cube
+// (improver/nbhood/nbhood.py:649-667): np.pad(mode="mean", stat_length=r) of
+// each 2-D slice, circular (2r+1)^2 windows, np.percentile(method="linear").
+//
+// One warp per grid point.  The N window values are held as order-preserving
+// uint32 keys in registers (KPL per lane); each requested order statistic is
+// found by a 32-step most-significant-bit-first bisection that counts keys
+// below the candidate with a warp reduction, so no sorting network and no
+// shared-memory traffic is needed in the selection itself.
+#include "nbh_common.cuh"
+
+namespace nbh {
+
+constexpr int kMaxPct = 32;
+
+struct PctParams {
+  const float* in;
+  float* out;
+  const float* padv;      // per slice: top[nx], bot[nx], left[ny+2r], right[ny+2r]
+  const int* offs;        // [N] packed (dy+r) << 16 | (dx+r) of kernel cells
+  long long n_slices;
+  int ny, nx, r, nb, N, n_pct;
+  int TW, TH, tiles_x, tiles_y;
+  int k_lo[kMaxPct];      // floor((N-1) * q)
+  float gamma[kMaxPct];   // fractional part (float32, numpy arithmetic)
+};
+
+__device__ __forceinline__ unsigned f2key(float f) {
+  unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Column / row pad means (np.pad mode="mean": axis 0 first, then axis 1 on
+// the already padded rows).  One block per slice.
+__global__ void pct_pad_kernel(const float* in, float* padv, int ny, int nx, int r) {
+  const long long s = blockIdx.x;
+  const float* a = in + s * (long long)ny * nx;
+  float* top = padv + s * (2LL * nx + 2LL * (ny + 2 * r));
+  float* bot = top + nx;
+  float* left = bot + nx;
+  float* right = left + (ny + 2 * r);
+  const int sy = min(r, ny), sx = min(r, nx);
+  for (int x = threadIdx.x; x < nx; x += blockDim.x) {
+    float t = 0.f, b = 0.f;
+    for (int i = 0; i < sy; ++i) { t += a[(long long)i * nx + x]; b += a[(long long)(ny - sy + i) * nx + x]; }
+    top[x] = t / (float)sy;
+    bot[x] = b / (float)sy;
+  }
+  __syncthreads();
+  for (int yp = threadIdx.x; yp < ny + 2 * r; yp += blockDim.x) {
+    const int y = yp - r;
+    const float* row = (y < 0) ? top : (y >= ny ? bot : a + (long long)y * nx);
+    double l = 0.0, rr = 0.0;
+    for (int j = 0; j < sx; ++j) { l += row[j]; rr += row[nx - sx + j]; }
+    left[yp] = (float)(l / sx);
+    right[yp] = (float)(rr / sx);
+  }
+}
+
+template <int KPL>
+__global__ void __launch_bounds__(256)
+percentile_kernel(const PctParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int r = p.r;
+  const int SW = p.TW + 2 * r, SH = p.TH + 2 * r;
+  unsigned* tile = reinterpret_cast<unsigned*>(smem_raw);      // [SH][SW] keys of the padded field
+  int* offs = reinterpret_cast<int*>(tile + (size_t)SH * SW);  // [32*KPL] tile-relative offsets
+
+  long long bid = blockIdx.x;
+  const int tx = (int)(bid % p.tiles_x); bid /= p.tiles_x;
+  const int ty = (int)(bid % p.tiles_y); bid /= p.tiles_y;
+  const long long s = bid;
+  const int x0 = tx * p.TW, y0 = ty * p.TH;
+  const float* a = p.in + s * (long long)p.ny * p.nx;
+  const float* top = p.padv + s * (2LL * p.nx + 2LL * (p.ny + 2 * r));
+  const float* bot = top + p.nx;
+  const float* left = bot + p.nx;
+  const float* right = left + (p.ny + 2 * r);
+
+  for (int i = threadIdx.x; i < SH * SW; i += blockDim.x) {
+    const int ly = i / SW, lx = i - ly * SW;
+    const int y = y0 + ly - r, x = x0 + lx - r;
+    float v;
+    if (x < 0) v = left[min(max(y, -r), p.ny + r - 1) + r];
+    else if (x >= p.nx) v = right[min(max(y, -r), p.ny + r - 1) + r];
+    else if (y < 0) v = top[x];
+    else if (y >= p.ny) v = bot[x];
+    else v = a[(long long)y * p.nx + x];
+    tile[i] = f2key(v);
+  }
+  for (int i = threadIdx.x; i < 32 * KPL; i += blockDim.x) {
+    if (i < p.N) {
+      const int o = p.offs[i];
+      offs[i] = (o >> 16) * SW + (o & 0xffff);
+    } else {
+      offs[i] = -1;
+    }
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  int my_off[KPL];
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) my_off[j] = offs[j * 32 + lane];
+
+  for (int pt = warp; pt < p.TW * p.TH; pt += nwarps) {
+    const int ly = pt / p.TW, lx = pt - ly * p.TW;
+    const int y = y0 + ly, x = x0 + lx;
+    if (y >= p.ny || x >= p.nx) continue;
+    const int base = ly * SW + lx;
+    unsigned key[KPL];
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) key[j] = my_off[j] >= 0 ? tile[base + my_off[j]] : 0xffffffffu;
+
+    for (int q = 0; q < p.n_pct; ++q) {
+      const int k = p.k_lo[q];
+      // k-th smallest key (0-based): MSB-first bisection
+      unsigned prefix = 0;
+#pragma unroll 1
+      for (int bit = 31; bit >= 0; --bit) {
+        const unsigned cand = prefix | (1u << bit);
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) cnt += key[j] < cand;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt <= k) prefix = cand;
+      }
+      // (k+1)-th: same value if duplicated, else the smallest key above
+      int cle = 0;
+      unsigned nxt = 0xffffffffu;
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        cle += key[j] <= prefix;
+        if (key[j] > prefix) nxt = min(nxt, key[j]);
+      }
+      cle = __reduce_add_sync(0xffffffffu, cle);
+      nxt = __reduce_min_sync(0xffffffffu, nxt);
+      const float lo = key2f(prefix);
+      const float hi = (k + 1 >= p.N || cle >= k + 2) ? lo : key2f(nxt);
+      // numpy _lerp (float32): a + (b-a)*t, and b - (b-a)*(1-t) where t >= 0.5
+      const float t = p.gamma[q];
+      const float diff = __fsub_rn(hi, lo);
+      float res = __fadd_rn(lo, __fmul_rn(diff, t));
+      if (t >= 0.5f) res = __fsub_rn(hi, __fmul_rn(diff, __fsub_rn(1.0f, t)));
+      if (lane == 0)
+        p.out[((s * p.n_pct + q) * p.ny + y) * (long long)p.nx + x] = res;
+    }
+  }
+}
+
+size_t percentiles_workspace_bytes(long long n_slices, int ny, int nx, int cells) {
+  const size_t nb = 2 * (size_t)cells + 1;
+  size_t pad = (size_t)n_slices * (2 * (size_t)nx + 2 * ((size_t)ny + 2 * cells)) * 4;
+  pad = (pad + 255) / 256 * 256;
+  return pad + nb * nb * 4 + 256;
+}
+
+template <int KPL>
+static int launch_pct(const PctParams& p, long long blocks, size_t smem, cudaStream_t st) {
+  auto kern = percentile_kernel<KPL>;
+  NBH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)blocks, 256, smem, st>>>(p);
+  NBH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int run_percentiles(const float* in, float* out, const float* pct, int n_pct, long long n_slices, int ny,
+                    int nx, int cells, int32_t* status, void* workspace, size_t workspace_bytes,
+                    cudaStream_t st) {
+  NBH_REQUIRE(in && out && pct && status && workspace, "null pointer argument");
+  NBH_REQUIRE(n_pct >= 1 && n_pct <= kMaxPct, "number of percentiles must be in [1, %d], got %d", kMaxPct,
+              n_pct);
+  NBH_REQUIRE(n_slices >= 1 && ny >= 1 && nx >= 1 && cells >= 1, "empty input");
+  NBH_REQUIRE(workspace_bytes >= percentiles_workspace_bytes(n_slices, ny, nx, cells), "workspace too small");
+  const int r = cells, nb = 2 * r + 1;
+  // kernel cell offsets, row-major like kernel > 0 boolean indexing (nbhood.py:646, 662)
+  static thread_local int h_offs[4096 * 8];
+  int N = 0;
+  for (int dy = -r; dy <= r; ++dy)
+    for (int dx = -r; dx <= r; ++dx)
+      if (dy * dy + dx * dx <= r * r) {
+        NBH_REQUIRE(N < (int)(sizeof(h_offs) / sizeof(int)), "percentile radius of %d cells is too large", r);
+        h_offs[N++] = ((dy + r) << 16) | (dx + r);
+      }
+  NBH_REQUIRE(N <= 32 * 72, "percentile neighbourhood of %d cells (radius %d) exceeds the supported %d", N, r,
+              32 * 72);
+  PctParams p;
+  memset(&p, 0, sizeof(p));
+  for (int q = 0; q < n_pct; ++q) {
+    NBH_REQUIRE(pct[q] >= 0.f && pct[q] <= 100.f, "Percentiles must be in the range [0, 100]");
+    // numpy: q32 = float32(p) / float32(100); vi = (N - 1) * q32 (float32)
+    const float q32 = pct[q] / 100.0f;
+    const float vi = (float)(N - 1) * q32;
+    const float fl = floorf(vi);
+    p.k_lo[q] = (int)fl;
+    p.gamma[q] = vi - fl;
+  }
+  unsigned char* base = reinterpret_cast<unsigned char*>(workspace);
+  size_t pad = (size_t)n_slices * (2 * (size_t)nx + 2 * ((size_t)ny + 2 * r)) * 4;
+  pad = (pad + 255) / 256 * 256;
+  float* padv = reinterpret_cast<float*>(base);
+  int* d_offs = reinterpret_cast<int*>(base + pad);
+  NBH_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int32_t), st));
+  NBH_CHECK_CUDA(cudaMemcpyAsync(d_offs, h_offs, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+  pct_pad_kernel<<<(unsigned)n_slices, 256, 0, st>>>(in, padv, ny, nx, r);
+
+  p.in = in; p.out = out; p.padv = padv; p.offs = d_offs;
+  p.n_slices = n_slices; p.ny = ny; p.nx = nx; p.r = r; p.nb = nb; p.N = N; p.n_pct = n_pct;
+  p.TW = 32; p.TH = 16;
+  p.tiles_x = (nx + p.TW - 1) / p.TW;
+  p.tiles_y = (ny + p.TH - 1) / p.TH;
+  const long long blocks = (long long)p.tiles_x * p.tiles_y * n_slices;
+  NBH_REQUIRE(blocks < (1LL << 31), "too many blocks");
+  const int kpl = (N + 31) / 32;
+  const int sizes[] = {1, 2, 4, 7, 10, 16, 24, 40, 72};
+  int pick = 72;
+  for (int s : sizes) if (s >= kpl) { pick = s; break; }
+  const size_t smem = (size_t)(p.TW + 2 * r) * (p.TH + 2 * r) * 4 + (size_t)32 * pick * 4;
+  switch (pick) {
+    case 1: return launch_pct<1>(p, blocks, smem, st);
+    case 2: return launch_pct<2>(p, blocks, smem, st);
+    case 4: return launch_pct<4>(p, blocks, smem, st);
+    case 7: return launch_pct<7>(p, blocks, smem, st);
+    case 10: return launch_pct<10>(p, blocks, smem, st);
+    case 16: return launch_pct<16>(p, blocks, smem, st);
+    case 24: return launch_pct<24>(p, blocks, smem, st);
+    case 40: return launch_pct<40>(p, blocks, smem, st);
+    default: return launch_pct<72>(p, blocks, smem, st);
+  }
+}
+
+}  // namespace nbh

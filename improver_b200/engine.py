@@ -1,0 +1,250 @@
+"""Tensor-level entry points of the B200 engine.
+
+PyTorch is used for device memory, streams and (elsewhere) torch.distributed;
+all arithmetic happens in libimprover_b200.so through the C ABI
+(include/improver_b200.h).  Inputs are CUDA float32 tensors laid out
+(..., y, x); nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NbhDesc, NbhThreshold
+
+MAX_THRESHOLDS_PER_LAUNCH = 8
+NAN_MESSAGE = "Error: NaN detected in input cube data"   # nbhood.py:168, threshold.py:665
+
+_workspaces = {}
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (improver_b200 has no CPU path)")
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def make_thresholds(thresholds: Sequence[Tuple[float, float, float, str]]):
+    """(value, lower bound, upper bound, comparison operator) -> NbhThreshold array."""
+    arr = (NbhThreshold * len(thresholds))()
+    for i, (val, lo, hi, op) in enumerate(thresholds):
+        arr[i].value, arr[i].lo, arr[i].hi = float(val), float(lo), float(hi)
+        arr[i].op = _lib.OPS[op] if isinstance(op, str) else int(op)
+    return arr
+
+
+def check_status(status: torch.Tensor) -> int:
+    """Synchronise on the status words of a launch; raise the reference's
+    ValueError if an unmasked NaN was read.  Returns the number of slices the
+    trimming fix-up touched."""
+    nan_flag, fixed = status.tolist()
+    if nan_flag:
+        raise ValueError(NAN_MESSAGE)
+    return fixed
+
+
+def neighbourhood(
+    data: torch.Tensor,
+    cells: int,
+    method: str = "square",
+    mask2d: Optional[torch.Tensor] = None,
+    mask_nd: Optional[torch.Tensor] = None,
+    weighted_mode: bool = False,
+    sum_only: bool = False,
+    thresholds=None,
+    collapse_members: bool = False,
+    wrap_x: bool = False,
+    want_mask: bool = False,
+    out: Optional[torch.Tensor] = None,
+):
+    """Neighbourhood sum/mean of every 2-D slice of `data`.
+
+    data            float32 CUDA (..., ny, nx); with collapse_members the
+                    LEADING axis holds the members (realizations) that are
+                    averaged after neighbourhooding.
+    mask2d          uint8/bool (ny, nx), non-zero = valid (mask_cube semantics).
+    mask_nd         uint8/bool like data, non-zero = masked (np.ma semantics).
+    thresholds      optional sequence of (value, lo, hi, op): the fuzzy
+                    threshold is applied to each value first and a threshold
+                    axis is inserted before (ny, nx).
+    Returns (out, out_mask or None, status).  status is an int32[2] CUDA
+    tensor; pass it to check_status() (this is the only synchronisation).
+    """
+    lib = _lib.load()
+    _require_cuda(data, "data")
+    if data.dtype != torch.float32:
+        raise TypeError("data must be float32")
+    if data.dim() < 2:
+        raise ValueError("data must have at least two dimensions (y, x)")
+    data = data.contiguous()
+    ny, nx = int(data.shape[-2]), int(data.shape[-1])
+    lead = tuple(int(s) for s in data.shape[:-2])
+    if collapse_members:
+        if not lead:
+            raise ValueError("collapse_members needs a leading member axis")
+        n_members, plane_shape = lead[0], lead[1:]
+    else:
+        n_members, plane_shape = 1, lead
+    n_planes = int(np.prod(plane_shape)) if plane_shape else 1
+    slice_elems = ny * nx
+    member_stride = n_planes * slice_elems if collapse_members else 0
+    if n_planes == 0 or slice_elems == 0:
+        raise ValueError("empty input")
+
+    thr_list = list(thresholds) if thresholds is not None else []
+    T = len(thr_list)
+    out_shape = plane_shape + ((T,) if T else ()) + (ny, nx)
+    if out is None:
+        out = torch.empty(out_shape, dtype=torch.float32, device=data.device)
+    elif tuple(out.shape) != out_shape or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError(f"out must be a contiguous float32 tensor of shape {out_shape}")
+    out_mask = torch.empty(out_shape, dtype=torch.uint8, device=data.device) if want_mask else None
+    status = torch.empty(2, dtype=torch.int32, device=data.device)
+
+    if mask2d is not None:
+        _require_cuda(mask2d, "mask2d")
+        if tuple(mask2d.shape) != (ny, nx):
+            raise ValueError("mask2d must have shape (ny, nx)")
+        mask2d = (mask2d != 0).to(torch.uint8).contiguous() if mask2d.dtype != torch.uint8 \
+            else mask2d.contiguous()
+    if mask_nd is not None:
+        _require_cuda(mask_nd, "mask_nd")
+        if collapse_members:
+            raise ValueError("mask_nd cannot be combined with collapse_members")
+        if tuple(mask_nd.shape) != tuple(data.shape):
+            raise ValueError("mask_nd must have the shape of data")
+        mask_nd = (mask_nd != 0).to(torch.uint8).contiguous() if mask_nd.dtype != torch.uint8 \
+            else mask_nd.contiguous()
+
+    flags = 0
+    if sum_only:
+        flags |= _lib.SUM_ONLY
+    if wrap_x:
+        flags |= _lib.WRAP_X
+    if weighted_mode:
+        flags |= _lib.WEIGHTED
+    if method == "square":
+        fn = lib.nbh_square_f32
+    elif method == "circular":
+        fn = lib.nbh_circular_f32
+    else:
+        raise ValueError("{} is not a valid neighbourhood_method.".format(method))
+
+    desc = NbhDesc()
+    desc.n_planes, desc.n_members, desc.ny, desc.nx = n_planes, n_members, ny, nx
+    desc.cells = int(cells)
+    desc.plane_stride, desc.member_stride = slice_elems, member_stride
+    desc.flags = flags
+    desc.mask2d = mask2d.data_ptr() if mask2d is not None else None
+    desc.mask_nd = mask_nd.data_ptr() if mask_nd is not None else None
+
+    stream = _stream_ptr()
+    with torch.cuda.device(data.device):
+        if T <= MAX_THRESHOLDS_PER_LAUNCH:
+            thr_arr = make_thresholds(thr_list) if T else None
+            desc.n_thresholds = T
+            desc.thresholds = thr_arr if T else None
+            ws = _workspace(data.device, lib.nbh_workspace_bytes(C.byref(desc)))
+            _lib.check(fn(C.byref(desc), data.data_ptr(), out.data_ptr(),
+                          out_mask.data_ptr() if want_mask else None, status.data_ptr(),
+                          ws.data_ptr(), ws.numel(), stream))
+        else:
+            # more thresholds than one launch group: chunks write into a
+            # staging tensor that is scattered into the threshold axis
+            acc_status = torch.zeros(2, dtype=torch.int32, device=data.device)
+            for t0 in range(0, T, MAX_THRESHOLDS_PER_LAUNCH):
+                chunk = thr_list[t0:t0 + MAX_THRESHOLDS_PER_LAUNCH]
+                sub, sub_mask, st = neighbourhood(
+                    data, cells, method, mask2d, mask_nd, weighted_mode, sum_only, chunk,
+                    collapse_members, wrap_x, want_mask)
+                out[..., t0:t0 + len(chunk), :, :] = sub
+                if want_mask:
+                    out_mask[..., t0:t0 + len(chunk), :, :] = sub_mask
+                acc_status = torch.maximum(acc_status, st)
+            status = acc_status
+    return out, out_mask, status
+
+
+def threshold(data: torch.Tensor, thresholds, mask_nd: Optional[torch.Tensor] = None,
+              collapse_leading: bool = False):
+    """Truth values of `data` against each threshold (threshold.py:643-713).
+
+    Returns (out float32 (T, ...), contrib int32 (...), status).  With
+    collapse_leading the leading axis is averaged over its unmasked members."""
+    lib = _lib.load()
+    _require_cuda(data, "data")
+    if data.dtype != torch.float32:
+        raise TypeError("data must be float32")
+    data = data.contiguous()
+    if collapse_leading:
+        n_collapse, pshape = int(data.shape[0]), tuple(data.shape[1:])
+    else:
+        n_collapse, pshape = 1, tuple(data.shape)
+    n_points = int(np.prod(pshape)) if pshape else 1
+    thr_list = list(thresholds)
+    T = len(thr_list)
+    out = torch.empty((T,) + pshape, dtype=torch.float32, device=data.device)
+    contrib = torch.empty(pshape, dtype=torch.int32, device=data.device)
+    status = torch.zeros(2, dtype=torch.int32, device=data.device)
+    if mask_nd is not None:
+        _require_cuda(mask_nd, "mask_nd")
+        mask_nd = (mask_nd != 0).to(torch.uint8).contiguous() if mask_nd.dtype != torch.uint8 \
+            else mask_nd.contiguous()
+    stream = _stream_ptr()
+    with torch.cuda.device(data.device):
+        for t0 in range(0, T, MAX_THRESHOLDS_PER_LAUNCH):
+            chunk = thr_list[t0:t0 + MAX_THRESHOLDS_PER_LAUNCH]
+            arr = make_thresholds(chunk)
+            st = torch.empty(2, dtype=torch.int32, device=data.device)
+            _lib.check(lib.nbh_threshold_f32(
+                data.data_ptr(), mask_nd.data_ptr() if mask_nd is not None else None,
+                out[t0:t0 + len(chunk)].data_ptr(), contrib.data_ptr(), arr, len(chunk),
+                n_collapse, n_points, st.data_ptr(), stream))
+            status = torch.maximum(status, st)
+    return out, contrib, status
+
+
+def neighbourhood_percentiles(data: torch.Tensor, cells: int, percentiles: Sequence[float]):
+    """Percentiles of the circular neighbourhood of every point
+    (nbhood.py:649-667).  data float32 (..., ny, nx) -> (..., P, ny, nx)."""
+    lib = _lib.load()
+    _require_cuda(data, "data")
+    if data.dtype != torch.float32:
+        raise TypeError("data must be float32")
+    data = data.contiguous()
+    ny, nx = int(data.shape[-2]), int(data.shape[-1])
+    lead = tuple(int(s) for s in data.shape[:-2])
+    n_slices = int(np.prod(lead)) if lead else 1
+    pcts = np.asarray(list(percentiles), dtype=np.float32)
+    out = torch.empty(lead + (len(pcts), ny, nx), dtype=torch.float32, device=data.device)
+    status = torch.empty(2, dtype=torch.int32, device=data.device)
+    ws = _workspace(data.device, lib.nbh_percentiles_workspace_bytes(n_slices, ny, nx, int(cells)))
+    with torch.cuda.device(data.device):
+        _lib.check(lib.nbh_percentiles_f32(
+            data.data_ptr(), out.data_ptr(), pcts.ctypes.data_as(C.POINTER(C.c_float)), len(pcts),
+            n_slices, ny, nx, int(cells), status.data_ptr(), ws.data_ptr(), ws.numel(),
+            _stream_ptr()))
+    return out, status
+
+
+def device_info():
+    lib = _lib.load()
+    sm, smem = C.c_int32(), C.c_int64()
+    _lib.check(lib.nbh_device_info(C.byref(sm), C.byref(smem)))
+    return sm.value, smem.value

@@ -1,0 +1,125 @@
+/*
+ * improver_b200 — C ABI of the B200 (sm_100a) neighbourhood-processing engine.
+ *
+ * This is the drop-in boundary for the hot path of metoppv/improver's
+ * `improver.nbhood` / `improver.threshold`.  The reference is
+ * pure Python: the "FFI" a maintainer would add is a ctypes binding (shown in
+ * INTEGRATION.md).  Every entry point takes plain pointers and sizes.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers owned by the caller unless marked
+ *     HOST; arrays are C-contiguous, spatial dims last: (..., y, x);
+ *   - `stream` is a cudaStream_t passed as void*; work is stream-ordered, no
+ *     entry point synchronises or allocates;
+ *   - return 0 on success, non-zero on error (message: nbh_last_error());
+ *   - float32 in / float32 out like the reference (FLOAT_DTYPE,
+ *     improver/metadata/constants/__init__.py:9); sums are accumulated in
+ *     float64 like improver/nbhood/nbhood.py:282-285.
+ */
+#ifndef IMPROVER_B200_H
+#define IMPROVER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBH_ABI_VERSION 1
+
+/* comparison operators, improver/utilities/probability_manipulation.py:15-66 */
+enum { NBH_OP_GT = 0, NBH_OP_GE = 1, NBH_OP_LT = 2, NBH_OP_LE = 3 };
+
+/* flags */
+enum {
+  NBH_SUM_ONLY = 1,   /* NeighbourhoodProcessing(sum_only=True), nbhood.py:188 */
+  NBH_WRAP_X   = 2,   /* extension: periodic x (global grids); no reference parity */
+  NBH_WEIGHTED = 4    /* circular weighted_mode, nbhood.py:55-92 */
+};
+
+/* One threshold with its fuzzy bounds (improver/threshold.py:302-333).
+ * lo == hi selects the deterministic comparison (threshold.py:438-439). */
+typedef struct NbhThreshold {
+  double value;
+  double lo;
+  double hi;
+  int32_t op;       /* NBH_OP_* */
+  int32_t _pad;
+} NbhThreshold;
+
+/* Description of one neighbourhood launch.
+ *
+ * Input is viewed as planes x members of 2-D (ny, nx) float32 slices:
+ *   slice(p, m) = in + p * plane_stride + m * member_stride      (elements)
+ * For NeighbourhoodProcessing.process (nbhood.py:457-463) every slice is its
+ * own plane (n_members = 1).  For the fused Threshold -> neighbourhood ->
+ * realization-mean chain, a plane is one lead time and the members are the
+ * realizations collapsed by the mean (cube_manipulation.py:93-131).
+ * Output: float32 (n_planes, max(n_thresholds,1), ny, nx).
+ */
+typedef struct NbhDesc {
+  int64_t n_planes;
+  int32_t n_members;
+  int32_t ny;
+  int32_t nx;
+  int32_t cells;            /* radius in grid cells: int(radius / spacing), spatial.py:152-156 */
+  int64_t plane_stride;
+  int64_t member_stride;
+  int32_t n_thresholds;     /* 0: neighbourhood of the input itself */
+  int32_t flags;
+  const NbhThreshold* thresholds;   /* HOST pointer, n_thresholds entries */
+  const uint8_t* mask2d;    /* (ny,nx) non-zero = valid point (mask_cube, nbhood.py:453-456) or NULL */
+  const uint8_t* mask_nd;   /* same shape as input, non-zero = MASKED (np.ma mask) or NULL;
+                               requires n_members == 1 */
+} NbhDesc;
+
+int nbh_version(void);
+const char* nbh_last_error(void);
+/* number of SMs and opt-in shared memory of the current device */
+int nbh_device_info(int32_t* sm_count, int64_t* smem_optin_bytes);
+
+/* Scratch the caller must provide (zero-initialisation not required). */
+size_t nbh_workspace_bytes(const NbhDesc* desc);
+
+/* Replaces NeighbourhoodProcessing._calculate_neighbourhood with method
+ * "square" (improver/nbhood/nbhood.py:244-409, boxsum at
+ * improver/utilities/neighbourhood_tools.py:129-211), optionally fused with
+ * Threshold._calculate_truth_value (improver/threshold.py:407-471) in front
+ * and the realization mean behind.
+ *   out       float32 (n_planes, T, ny, nx)
+ *   out_mask  uint8 same shape as out or NULL: 1 where the reference's re_mask
+ *             would mask the point (nbhood.py:314-315)
+ *   status    int32[2] device: [0] = 1 if an unmasked NaN was read
+ *             (nbhood.py:167-168), [1] = number of slices the trimming fix-up touched
+ */
+int nbh_square_f32(const NbhDesc* desc, const float* in, float* out, uint8_t* out_mask,
+                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same contract for method "circular" (nbhood.py:55-92 kernel,
+ * scipy.ndimage.correlate(mode="nearest") at nbhood.py:401). */
+int nbh_circular_f32(const NbhDesc* desc, const float* in, float* out, uint8_t* out_mask,
+                     int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces GeneratePercentilesFromANeighbourhood.pad_and_unpad_cube
+ * (nbhood.py:649-667): in float32 (n_slices, ny, nx) ->
+ * out float32 (n_slices, n_pct, ny, nx); pct: HOST float32 percentiles. */
+int nbh_percentiles_f32(const float* in, float* out, const float* pct, int32_t n_pct,
+                        int64_t n_slices, int32_t ny, int32_t nx, int32_t cells,
+                        int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+size_t nbh_percentiles_workspace_bytes(int64_t n_slices, int32_t ny, int32_t nx, int32_t cells);
+
+/* Replaces the Threshold.process hot loop (improver/threshold.py:643-713).
+ *   in        float32 (n_collapse, n_points) ; mask_nd uint8 same shape or NULL
+ *   out       float32 (T, n_points): mean truth value over unmasked members
+ *   contrib   int32 (n_points) or NULL: number of unmasked members (threshold.py:679)
+ *   n_collapse = 1 when no coordinate is collapsed.
+ */
+int nbh_threshold_f32(const float* in, const uint8_t* mask_nd, float* out, int32_t* contrib,
+                      const NbhThreshold* thresholds, int32_t n_thresholds,
+                      int64_t n_collapse, int64_t n_points, int32_t* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMPROVER_B200_H */
