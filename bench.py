@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Benchmark of the neighbourhood hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[2], the configuration the
+headline metric is quoted on — fused fuzzy Threshold -> square neighbourhood
+(radius 10 km = 5 cells) -> realization mean on an 18-member x 36-lead-time
+UK 2 km (970 x 1042) float32 cube, synthetic gamma(2, 1.5) "rain rate".
+One step = one pass of the hot path over that whole cube.  Unit:
+gridpoint-evaluations/s, one evaluation = one (realization, threshold,
+lead-time, y, x) neighbourhood result.
+
+Multi-GPU: every rank processes its own cube (weak scaling, lead-time slices
+are independent, no data-path collective); value = evaluations of all ranks /
+max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R, L, NY, NX = 18, 36, 970, 1042
+CELLS = 5
+THRESHOLD, FUZZY = 2.0, 0.7
+BOUNDS = (THRESHOLD * FUZZY, THRESHOLD * (2.0 - FUZZY))
+T = 1
+EVALS_PER_STEP = R * T * L * NY * NX
+ALGO_BYTES_PER_STEP = 4 * NY * NX * L * (R + T)
+METRIC = "neighbourhood gridpoint-evals/s"
+UNIT = "gridpoint-evals/s"
+WORKLOAD = ("fused fuzzy Threshold(2.0, ff=0.7) -> square nbhood r=5 cells (10 km) -> mean over "
+            "18 realizations; 36 lead times; UK 2 km grid 970x1042; float32")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                     "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thr.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active")
+                                                          for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- #
+# CPU side (oracle = port of the reference's numpy/scipy path)
+# ----------------------------------------------------------------------------- #
+def synth_host(n_lead: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    return rng.gamma(2.0, 1.5, (R, n_lead, NY, NX)).astype(np.float32)
+
+
+def _cpu_one_lead(args):
+    seed, = args
+    from oracle import nbhood_oracle as orc
+    data = synth_host(1, seed)
+    t0 = time.perf_counter()
+    orc.threshold_square_mean(data, [THRESHOLD], [BOUNDS], ">", CELLS)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(n_lead: int, procs: int):
+    """Oracle port of the reference chain on `n_lead` lead times spread over
+    `procs` processes (slices are independent: how operational suites use the
+    reference).  Returns evals/s (wall clock of the pool) and the sample text."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_one_lead, [(100 + i,) for i in range(procs)][:1])     # start-up / imports
+        t0 = time.perf_counter()
+        pool.map(_cpu_one_lead, [(200 + i,) for i in range(n_lead)], chunksize=1)
+        wall = time.perf_counter() - t0
+    evals = R * T * n_lead * NY * NX
+    return evals / wall, f"{n_lead} of {L} lead times x {R} members, {procs} processes"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    sample = ""
+    for _ in range(args.warmup):
+        cpu_reference_rate(max(1, cores // 4), cores)
+    for _ in range(args.steps):
+        v, sample = cpu_reference_rate(cores, cores)
+        vals.append(v)
+    value = float(np.mean(vals))
+    step_ms = (R * T * cores * NY * NX) / value * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64-accum",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample + " (oracle/nbhood_oracle.py: numpy/scipy restatement of "
+                         "the reference path; the Python reference cannot travel to the GPU box)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- #
+# GPU side
+# ----------------------------------------------------------------------------- #
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from improver_b200 import engine, pipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # synthetic gamma(2, 1.5) cube generated on the device (sum of two exponentials)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3 + rank)
+    cube = torch.empty((R, L, NY, NX), dtype=torch.float32, device=dev)
+    for r in range(R):
+        u = torch.rand((2, L, NY, NX), generator=gen, device=dev).clamp_min_(1e-12)
+        cube[r] = -1.5 * (torch.log(u[0]) + torch.log(u[1]))
+        del u
+    thr = [(THRESHOLD, BOUNDS[0], BOUNDS[1], ">")]
+    out = torch.empty((L, T, NY, NX), dtype=torch.float32, device=dev)
+
+    def step():
+        _, _, status = engine.neighbourhood(cube, CELLS, method="square", thresholds=thr,
+                                            collapse_members=True, out=out)
+        return status
+
+    for _ in range(max(args.warmup, 3)):
+        status = step()
+    engine.check_status(status)
+
+    # ---- device-resident timing (value) -------------------------------------
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            status = step()
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    engine.check_status(status)
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tmax.item()) / args.steps
+    value = EVALS_PER_STEP * world / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel duration (roofline) --------------------------------
+    kernel_ms = pipeline.time_main_kernel(lambda: step(), reps=max(3, args.steps))
+    peak, peak_src = peaks()
+    achieved = ALGO_BYTES_PER_STEP / (kernel_ms * 1e-3) / 1e9
+
+    # ---- end to end through the public API with HOST buffers ----------------
+    e2e_steps = max(1, min(args.steps, 3))
+    host_in = pipeline.pinned_like(cube)            # pinned host copy of this rank's cube
+    host_in.copy_(cube)
+    torch.cuda.synchronize()
+    host_out = None
+    for _ in range(1):
+        host_out = pipeline.threshold_neighbourhood_mean_host(
+            host_in, [THRESHOLD], [BOUNDS], ">", CELLS, method="square")
+    barrier()
+    ev0.record()
+    for _ in range(e2e_steps):
+        host_out = pipeline.threshold_neighbourhood_mean_host(
+            host_in, [THRESHOLD], [BOUNDS], ">", CELLS, method="square")
+    ev1.record()
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = EVALS_PER_STEP * world / (float(e2e_ms.item()) / e2e_steps * 1e-3)
+    h2d = cube.numel() * 4
+    d2h = out.numel() * 4 + 8
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 accumulation)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "shape": [R, L, NY, NX], "cells": CELLS,
+                       "thresholds": T, "l2": "inputs (2.6 GB/step) larger than L2; no flush needed",
+                       "sharding": "one full cube per GPU, lead-time slices independent, no collective"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "improver_b200.pipeline.threshold_neighbourhood_mean_host (pinned host in/out)"},
+            "gpu_launches": pipeline.LAUNCHES_PER_FUSED_CALL * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "frac_of_8TBs": achieved / 8000.0,
+                         "traffic": pipeline.recorded_traffic_bytes(),
+                         "kernel": "nbh::square_kernel<2,2,false>", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes": ALGO_BYTES_PER_STEP, "peak_source": peak_src},
+            "hbm_gbs": achieved,
+        }
+    # CPU baseline beside it (rank 0, N == 1 only)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n_lead = max(1, min(cores, 16))
+        v, sample = cpu_reference_rate(n_lead, min(cores, n_lead))
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": min(cores, n_lead), "kind": "port",
+                                "sample": sample}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

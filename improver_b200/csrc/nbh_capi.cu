@@ -16,10 +16,25 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_e0 = nullptr, g_prof_e1 = nullptr;
+static bool g_prof_valid = false;
+
+ProfileScope::ProfileScope(cudaStream_t s) : st(s), on(g_prof_on) {
+  if (!on) return;
+  if (!g_prof_e0) { cudaEventCreate(&g_prof_e0); cudaEventCreate(&g_prof_e1); }
+  cudaEventRecord(g_prof_e0, st);
+}
+ProfileScope::~ProfileScope() {
+  if (!on) return;
+  cudaEventRecord(g_prof_e1, st);
+  g_prof_valid = true;
+}
+
 // Host preparation of one threshold, mirroring the dtype handling of
 // improver/threshold.py:434 (threshold cast to the float32 data dtype) and
 // numpy's weak-scalar promotion of the python-float fuzzy bounds.
-int make_thr_dev(const NbhThreshold& h, ThrDev* d) {
+int make_thr_dev(const NbhThreshold& h, ThrDev* d, bool ma_arith) {
   memset(d, 0, sizeof(*d));
   NBH_REQUIRE(h.op >= NBH_OP_GT && h.op <= NBH_OP_LE, "unknown comparison operator code %d", h.op);
   d->op = h.op;
@@ -30,7 +45,8 @@ int make_thr_dev(const NbhThreshold& h, ThrDev* d) {
   }
   NBH_REQUIRE(h.lo <= h.value && h.value <= h.hi, "Threshold must be within bounds: !( %g <= %g <= %g )",
               h.lo, h.value, h.hi);
-  d->mode = 2;
+  d->mode = ma_arith ? 3 : 2;
+  d->lo64 = h.lo;
   d->lo = (float)h.lo;
   const float hi = (float)h.hi;
   d->den_lo = d->thr - d->lo;
@@ -61,6 +77,20 @@ extern "C" {
 int nbh_version(void) { return NBH_ABI_VERSION; }
 
 const char* nbh_last_error(void) { return nbh::g_err; }
+
+int nbh_profile_enable(int on) {
+  nbh::g_prof_on = on != 0;
+  nbh::g_prof_valid = false;
+  return 0;
+}
+
+int nbh_profile_last_ms(float* ms) {
+  NBH_REQUIRE(ms != nullptr, "null pointer argument");
+  NBH_REQUIRE(nbh::g_prof_valid, "no profiled launch recorded");
+  NBH_CHECK_CUDA(cudaEventSynchronize(nbh::g_prof_e1));
+  NBH_CHECK_CUDA(cudaEventElapsedTime(ms, nbh::g_prof_e0, nbh::g_prof_e1));
+  return 0;
+}
 
 int nbh_device_info(int32_t* sm_count, int64_t* smem_optin_bytes) {
   int dev = 0, n = 0, s = 0;

@@ -328,6 +328,7 @@ int run_circular(const NbhDesc* d, const float* in, float* out, uint8_t* out_mas
   const long long blocks = (long long)p.n_strips * p.n_ysegs * p.n_thr * d->n_planes;
   NBH_REQUIRE(blocks < (1LL << 31), "too many blocks (%lld); split the launch", blocks);
   const size_t smem = smem_for(tx);
+  ProfileScope prof(st);
   switch (tm) {
     case 0: return launch_circ_tm<0>(p, tx, smem, blocks, masknd, weighted, st);
     case 1: return launch_circ_tm<1>(p, tx, smem, blocks, masknd, weighted, st);

@@ -41,8 +41,9 @@ struct ThrDev {
   float rcp_lo;   // RN(1 / den_lo)       for the exact division sequence
   float den_hi;   // float32(bounds[1]) - thr
   float rcp_hi;
-  int mode;       // 0 raw data, 1 deterministic compare, 2 fuzzy
+  int mode;       // 0 raw data, 1 deterministic compare, 2 fuzzy, 3 fuzzy with np.ma arithmetic
   int op;         // NBH_OP_*
+  double lo64;    // bounds[0] unrounded (np.ma arithmetic promotes to float64)
 };
 
 struct ThrSet {
@@ -50,7 +51,7 @@ struct ThrSet {
   int n;          // 0 => raw
 };
 
-int make_thr_dev(const NbhThreshold& h, ThrDev* d);
+int make_thr_dev(const NbhThreshold& h, ThrDev* d, bool ma_arith = false);
 
 // Correctly rounded a / den for 0 <= a <= den, den normal, using the host
 // rounded reciprocal (Markstein: q0 = a*r; rem = a - den*q0 exact via FMA;
@@ -74,6 +75,20 @@ __device__ __forceinline__ float truth_value(float d, const ThrDev& p) {
       default: b = d <= p.thr; break;
     }
     return b ? 1.0f : 0.0f;
+  }
+  if (p.mode == 3) {
+    // Masked-array input: numpy.ma wraps the python-float operands in 0-d
+    // float64 arrays, so under NumPy 2 promotion the reference evaluates the
+    // rescale in float64 (the float32 scalar subtractions thr-lo / hi-thr and
+    // data-thr stay float32) and rounds once at the end (threshold.py:441-471).
+    const bool below = d < p.thr;
+    const double a = below ? ((double)d - p.lo64) : (double)__fsub_rn(d, p.thr);
+    const double den = below ? (double)p.den_lo : (double)p.den_hi;
+    const double off = below ? 0.0 : 0.5;
+    double v = a * 0.5 / den + off;
+    v = fmin(fmax(v, off), off + 0.5);
+    if (p.op >= NBH_OP_LT) v = 1.0 - v;
+    return (float)v;
   }
   // fuzzy: where(d < thr, clip((d-lo)*0.5/(thr-lo) + 0, 0, .5),
   //                        clip((d-thr)*0.5/(hi-thr) + .5, .5, 1))
@@ -130,6 +145,14 @@ template <> struct VecLoad<4> {
     uchar4 t = __ldg(reinterpret_cast<const uchar4*>(p));
     m[0] = t.x; m[1] = t.y; m[2] = t.z; m[3] = t.w;
   }
+};
+
+// bench.py measurement aid: events around the dominant kernel of a call
+struct ProfileScope {
+  cudaStream_t st;
+  bool on;
+  explicit ProfileScope(cudaStream_t s);
+  ~ProfileScope();
 };
 
 inline int sm_count() {

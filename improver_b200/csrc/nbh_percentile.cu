@@ -220,6 +220,7 @@ int run_percentiles(const float* in, float* out, const float* pct, int n_pct, lo
   int pick = 72;
   for (int s : sizes) if (s >= kpl) { pick = s; break; }
   const size_t smem = (size_t)(p.TW + 2 * r) * (p.TH + 2 * r) * 4 + (size_t)32 * pick * 4;
+  ProfileScope prof(st);
   switch (pick) {
     case 1: return launch_pct<1>(p, blocks, smem, st);
     case 2: return launch_pct<2>(p, blocks, smem, st);

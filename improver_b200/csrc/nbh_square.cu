@@ -592,9 +592,10 @@ int fill_thresholds(const NbhDesc& d, ThrSet* ts, int* tm) {
   ts->n = d.n_thresholds;
   *tm = 0;
   for (int i = 0; i < d.n_thresholds; ++i) {
-    if (make_thr_dev(d.thresholds[i], &ts->t[i])) return 1;
-    if (i == 0) *tm = ts->t[i].mode;
-    NBH_REQUIRE(ts->t[i].mode == *tm, "fuzzy and deterministic thresholds cannot be mixed in one launch");
+    if (make_thr_dev(d.thresholds[i], &ts->t[i], d.mask_nd != nullptr)) return 1;
+    const int m = ts->t[i].mode == 3 ? 2 : ts->t[i].mode;
+    if (i == 0) *tm = m;
+    NBH_REQUIRE(m == *tm, "fuzzy and deterministic thresholds cannot be mixed in one launch");
   }
   return 0;
 }
@@ -642,10 +643,13 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   const long long blocks = (long long)pl.n_strips * pl.n_ysegs * p.n_thr * d->n_planes;
   NBH_REQUIRE(blocks < (1LL << 31), "too many blocks (%lld); split the launch", blocks);
   int rc;
-  switch (pl.vec) {
-    case 4: rc = launch_square_v<4>(p, pl, blocks, tm, masknd, st); break;
-    case 2: rc = launch_square_v<2>(p, pl, blocks, tm, masknd, st); break;
-    default: rc = launch_square_v<1>(p, pl, blocks, tm, masknd, st); break;
+  {
+    ProfileScope prof(st);
+    switch (pl.vec) {
+      case 4: rc = launch_square_v<4>(p, pl, blocks, tm, masknd, st); break;
+      case 2: rc = launch_square_v<2>(p, pl, blocks, tm, masknd, st); break;
+      default: rc = launch_square_v<1>(p, pl, blocks, tm, masknd, st); break;
+    }
   }
   if (rc) return rc;
   if (!sum_only) {

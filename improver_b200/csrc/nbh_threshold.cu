@@ -75,7 +75,7 @@ int run_threshold(const float* in, const uint8_t* mask_nd, float* out, int32_t* 
   memset(&p, 0, sizeof(p));
   p.thr.n = n_thresholds;
   for (int i = 0; i < n_thresholds; ++i)
-    if (make_thr_dev(thresholds[i], &p.thr.t[i])) return 1;
+    if (make_thr_dev(thresholds[i], &p.thr.t[i], mask_nd != nullptr)) return 1;
   p.in = in; p.mask_nd = mask_nd; p.out = out; p.contrib = contrib; p.status = status;
   p.n_collapse = n_collapse; p.n_points = n_points;
   NBH_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int32_t), st));

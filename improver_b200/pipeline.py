@@ -1,0 +1,112 @@
+"""Host-facing pipeline of the fused chain and measurement helpers.
+
+`threshold_neighbourhood_mean_host` is the call a user of the reference makes
+when the cube lives in host memory: it streams lead-time chunks through pinned
+buffers (H2D on a copy stream, kernels on the compute stream, D2H of the much
+smaller result), so the PCIe copy overlaps the kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+
+LAUNCHES_PER_FUSED_CALL = 4     # init_stats, square_kernel, square_stats, square_fixup
+
+
+def pinned_like(t: torch.Tensor) -> torch.Tensor:
+    return torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+
+
+def threshold_neighbourhood_mean_host(host_in, thresholds: Sequence[float], bounds, comparison: str,
+                                      cells: int, method: str = "square", mask2d=None,
+                                      chunk_leads: int = 6, device=None):
+    """Fuzzy threshold -> neighbourhood -> realization mean for a HOST cube.
+
+    host_in   float32 (R, L, ny, nx) numpy array or (preferably pinned) CPU tensor
+    returns   float32 (L, T, ny, nx) pinned CPU tensor
+    Raises ValueError("Error: NaN detected in input cube data") like the
+    reference plugins (nbhood.py:167-168)."""
+    if isinstance(host_in, np.ndarray):
+        host_in = torch.from_numpy(np.ascontiguousarray(host_in, dtype=np.float32))
+    if host_in.is_cuda or host_in.dtype != torch.float32 or host_in.dim() != 4:
+        raise TypeError("host_in must be a float32 CPU array of shape (R, L, ny, nx)")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    R, L, ny, nx = (int(s) for s in host_in.shape)
+    T = len(thresholds)
+    thr = [(t, b[0], b[1], comparison) for t, b in zip(thresholds, bounds)]
+    out_host = torch.empty((L, T, ny, nx), dtype=torch.float32, pin_memory=True)
+    m2 = None
+    if mask2d is not None:
+        m2 = torch.as_tensor(np.asarray(mask2d) != 0).to(torch.uint8).to(dev)
+    chunk = max(c for c in range(1, max(1, min(chunk_leads, L)) + 1) if L % c == 0)
+    bufs = [torch.empty((R, chunk, ny, nx), dtype=torch.float32, device=dev) for _ in range(2)]
+    outs = [torch.empty((chunk, T, ny, nx), dtype=torch.float32, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    compute = torch.cuda.current_stream(dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    drained = [torch.cuda.Event() for _ in range(2)]
+    statuses = []
+    n_chunks = L // chunk
+    for i in range(n_chunks):
+        b = i & 1
+        l0, l1 = i * chunk, (i + 1) * chunk
+        with torch.cuda.stream(copy_stream):
+            if i >= 2:
+                copy_stream.wait_event(consumed[b])     # kernel that read bufs[b] has finished
+            for r in range(R):
+                bufs[b][r].copy_(host_in[r, l0:l1], non_blocking=True)
+            copied[b].record(copy_stream)
+        compute.wait_event(copied[b])
+        if i >= 2:
+            compute.wait_event(drained[b])              # outs[b] has been copied back
+        _, _, st = engine.neighbourhood(bufs[b], cells, method=method, mask2d=m2, thresholds=thr,
+                                        collapse_members=True, out=outs[b])
+        statuses.append(st)
+        consumed[b].record(compute)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])
+            out_host[l0:l1].copy_(outs[b], non_blocking=True)
+            drained[b].record(copy_stream)
+    status = torch.stack(statuses).amax(dim=0)
+    compute.wait_stream(copy_stream)
+    engine.check_status(status)          # D2H read of the status words: synchronises
+    torch.cuda.current_stream(dev).synchronize()
+    return out_host
+
+
+def time_main_kernel(fn, reps: int = 5) -> float:
+    """Average duration (ms) of the dominant kernel of `fn()`'s native call,
+    measured with CUDA events recorded inside the library on the launching
+    stream (nbh_profile_enable / nbh_profile_last_ms)."""
+    lib = _lib.load()
+    lib.nbh_profile_enable(1)
+    total = 0.0
+    try:
+        for _ in range(reps):
+            fn()
+            ms = C.c_float()
+            _lib.check(lib.nbh_profile_last_ms(C.byref(ms)))
+            total += ms.value
+    finally:
+        lib.nbh_profile_enable(0)
+    return total / reps
+
+
+def recorded_traffic_bytes():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu
+    capture (profiles/roofline.json), or None if no capture has been made."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles",
+                        "roofline.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh).get("square_fused_traffic_bytes")
+    except (OSError, ValueError):
+        return None

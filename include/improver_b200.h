@@ -119,6 +119,13 @@ int nbh_threshold_f32(const float* in, const uint8_t* mask_nd, float* out, int32
                       const NbhThreshold* thresholds, int32_t n_thresholds,
                       int64_t n_collapse, int64_t n_points, int32_t* status, void* stream);
 
+/* Measurement aid (bench.py roofline): when enabled, the dominant kernel of
+ * the next nbh_square_f32 / nbh_circular_f32 / nbh_percentiles_f32 call is
+ * bracketed by CUDA events on the caller's stream.  nbh_profile_last_ms
+ * synchronises on those events and returns the kernel's duration. */
+int nbh_profile_enable(int on);
+int nbh_profile_last_ms(float* ms);
+
 #ifdef __cplusplus
 }
 #endif
