@@ -48,14 +48,16 @@ int make_thr_dev(const NbhThreshold& h, ThrDev* d, bool ma_arith) {
   d->mode = ma_arith ? 3 : 2;
   d->lo64 = h.lo;
   d->lo = (float)h.lo;
-  const float hi = (float)h.hi;
+  d->hi = (float)h.hi;
   d->den_lo = d->thr - d->lo;
-  d->den_hi = hi - d->thr;
+  d->den_hi = d->hi - d->thr;
   // rescale() raises on a zero input range (rescale.py:50-53)
   NBH_REQUIRE(d->den_lo != 0.f && d->den_hi != 0.f,
               "Cannot rescale a zero input range (fuzzy bound equals the threshold in float32)");
-  d->rcp_lo = (float)(1.0 / (double)d->den_lo);
-  d->rcp_hi = (float)(1.0 / (double)d->den_hi);
+  d->den2_lo = 2.0f * d->den_lo;
+  d->den2_hi = 2.0f * d->den_hi;
+  d->rcph_lo = (float)(0.5 / (double)d->den_lo);
+  d->rcph_hi = (float)(0.5 / (double)d->den_hi);
   return 0;
 }
 

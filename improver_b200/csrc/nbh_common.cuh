@@ -37,10 +37,11 @@ constexpr int kMaxThresholds = 8;   // thresholds evaluated per launch group
 struct ThrDev {
   float thr;      // float32(threshold)                       threshold.py:434
   float lo;       // float32(bounds[0])   subtracted below thr
+  float hi;       // float32(bounds[1])
   float den_lo;   // thr - lo             (float32 subtraction)
-  float rcp_lo;   // RN(1 / den_lo)       for the exact division sequence
   float den_hi;   // float32(bounds[1]) - thr
-  float rcp_hi;
+  float den2_lo, den2_hi;   // 2 * den
+  float rcph_lo, rcph_hi;   // RN(0.5 / den), for the exact division sequence
   int mode;       // 0 raw data, 1 deterministic compare, 2 fuzzy, 3 fuzzy with np.ma arithmetic
   int op;         // NBH_OP_*
   double lo64;    // bounds[0] unrounded (np.ma arithmetic promotes to float64)
@@ -53,20 +54,16 @@ struct ThrSet {
 
 int make_thr_dev(const NbhThreshold& h, ThrDev* d, bool ma_arith = false);
 
-// Correctly rounded a / den for 0 <= a <= den, den normal, using the host
-// rounded reciprocal (Markstein: q0 = a*r; rem = a - den*q0 exact via FMA;
-// q = q0 + rem*r).  Matches numpy's IEEE float32 division; checked against the
-// oracle bit for bit in tests/test_gpu_threshold.py.
-__device__ __forceinline__ float div_exact(float a, float den, float rcp) {
-  float q0 = __fmul_rn(a, rcp);
-  float rem = __fmaf_rn(-den, q0, a);
-  return __fmaf_rn(rem, rcp, q0);
-}
-
+// Exact division: with r = RN(1/(2 den)) from the host, q0 = a*r,
+// rem = a - 2den*q0 (exact, FMA), q = q0 + rem*r is the correctly rounded
+// a/(2 den) (Markstein).  Checked bit for bit against numpy in the GPU tests.
 // Threshold._calculate_truth_value for one unmasked value (threshold.py:407-471).
-__device__ __forceinline__ float truth_value(float d, const ThrDev& p) {
-  if (p.mode == 0) return d;
-  if (p.mode == 1) {
+// MODE: 0 raw data, 1 deterministic comparison, 2 fuzzy (float32 arithmetic),
+// 3 fuzzy with numpy.ma arithmetic.
+template <int MODE>
+__device__ __forceinline__ float truth_value_t(float d, const ThrDev& p) {
+  if (MODE == 0) return d;
+  if (MODE == 1) {
     bool b;
     switch (p.op) {
       case NBH_OP_GT: b = d > p.thr; break;
@@ -76,7 +73,7 @@ __device__ __forceinline__ float truth_value(float d, const ThrDev& p) {
     }
     return b ? 1.0f : 0.0f;
   }
-  if (p.mode == 3) {
+  if (MODE == 3) {
     // Masked-array input: numpy.ma wraps the python-float operands in 0-d
     // float64 arrays, so under NumPy 2 promotion the reference evaluates the
     // rescale in float64 (the float32 scalar subtractions thr-lo / hi-thr and
@@ -92,20 +89,32 @@ __device__ __forceinline__ float truth_value(float d, const ThrDev& p) {
   }
   // fuzzy: where(d < thr, clip((d-lo)*0.5/(thr-lo) + 0, 0, .5),
   //                        clip((d-thr)*0.5/(hi-thr) + .5, .5, 1))
+  // Clamping the data to [lo, hi] first is equivalent to the reference's clip
+  // of the quotient (float32 subtraction, division by den > 0 and *0.5 are
+  // all monotone) and keeps +-inf inputs finite.  The *0.5 is folded into the
+  // exact division: RN(a*0.5/den) = a/(2 den) correctly rounded.
+  const float dc = fminf(fmaxf(d, p.lo), p.hi);
   const bool below = d < p.thr;
   const float base = below ? p.lo : p.thr;
-  const float den = below ? p.den_lo : p.den_hi;
-  const float rcp = below ? p.rcp_lo : p.rcp_hi;
+  const float den2 = below ? p.den2_lo : p.den2_hi;     // 2 * denominator
+  const float rcph = below ? p.rcph_lo : p.rcph_hi;     // RN(0.5 / denominator)
   const float off = below ? 0.0f : 0.5f;
-  float a = __fsub_rn(d, base);
-  // clamping the numerator to [0, den] is equivalent to the reference's clip
-  // of the quotient (division by den > 0 and *0.5 are monotone) and keeps
-  // +-inf inputs finite.
-  a = fminf(fmaxf(a, 0.0f), den);
-  float ah = __fmul_rn(a, 0.5f);
-  float v = __fadd_rn(div_exact(ah, den, rcp), off);
+  const float a = __fsub_rn(dc, base);
+  const float q0 = __fmul_rn(a, rcph);
+  const float rem = __fmaf_rn(-den2, q0, a);
+  float v = __fadd_rn(__fmaf_rn(rem, rcph, q0), off);
   if (p.op >= NBH_OP_LT) v = __fsub_rn(1.0f, v);     // threshold.py:468-469
   return v;
+}
+
+// runtime-dispatched form (un-fused threshold kernel, fix-up kernels)
+__device__ __forceinline__ float truth_value(float d, const ThrDev& p) {
+  switch (p.mode) {
+    case 0: return d;
+    case 1: return truth_value_t<1>(d, p);
+    case 2: return truth_value_t<2>(d, p);
+    default: return truth_value_t<3>(d, p);
+  }
 }
 
 __device__ __forceinline__ float max_nan(float a, float b) {

@@ -12,289 +12,9 @@
 // columns, no synchronisation), and (3) per output row does the horizontal
 // window sum as a difference of a float64 row prefix built with a warp-shuffle
 // scan, normalises by the valid-cell count and stores float32.
-#include "nbh_common.cuh"
+#include "nbh_square_warp.cuh"
 
 namespace nbh {
-
-struct SliceStats {      // exact per-slice statistics, only built for suspicious slices
-  int y0min, y0max, x0min, x0max;   // bbox of v != 0
-  int y1min, y1max, x1min, x1max;   // bbox of v != 1
-  int vmin_key, vmax_key;           // ordered-int keys of nanmin / nanmax of the slice
-};
-
-struct SqParams {
-  const float* in;
-  float* out;
-  uint8_t* out_mask;
-  const uint8_t* mask2d;
-  const uint8_t* mask_nd;
-  const double* rcp_count;   // (ny,nx) 1/count for mask2d launches
-  int32_t* status;
-  unsigned* edge_flags;      // [(plane*R + m) * T + t]
-  SliceStats* stats;
-  long long plane_stride, member_stride;
-  long long n_planes;
-  int n_members, ny, nx, r, nb;
-  int flags;
-  int W, WS, hl, n_strips, n_ysegs, seg_rows;
-  int n_thr;                 // max(n_thresholds, 1)
-  double inv_members;
-  ThrSet thr;
-};
-
-__device__ __forceinline__ int pidx(int c, int cpl_shift) { return c + (c >> cpl_shift); }
-
-__device__ __forceinline__ int float_key(float f) {
-  int b = __float_as_int(f);
-  return b >= 0 ? b : b ^ 0x7fffffff;
-}
-__device__ __forceinline__ float key_float(int k) {
-  return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
-}
-
-// ---------------------------------------------------------------------------
-// Main kernel
-// ---------------------------------------------------------------------------
-template <int VEC, int TM, bool MASKND>
-__global__ void __launch_bounds__(256)
-square_kernel(const SqParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int TX = blockDim.x;
-  const int nwarps = TX >> 5;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int WS = p.WS, nb = p.nb, r = p.r;
-  const int CPL = WS >> 5;                 // columns per lane in the horizontal pass (power of 2)
-  const int CPS = 31 - __clz(CPL);         // log2(CPL)
-  const int WSP = WS + 32;                 // padded row length (one pad per lane group)
-
-  // shared memory carve-up
-  double* vbuf = reinterpret_cast<double*>(smem_raw);                 // [nwarps][WSP]
-  double* rtab = vbuf + (size_t)nwarps * WSP;                         // [nb + 1]
-  float* ring = reinterpret_cast<float*>(rtab + ((nb + 2) & ~1));     // [nb][WS]
-  float* cring = ring + (size_t)nb * WS;                              // MASKND: [nb][WS]
-  float* cbuf = cring + (MASKND ? (size_t)nb * WS : 0);               // MASKND: [nwarps][WSP]
-
-  // decode block -> (plane, t, yseg, strip)
-  long long bid = blockIdx.x;
-  const int strip = (int)(bid % p.n_strips); bid /= p.n_strips;
-  const int yseg = (int)(bid % p.n_ysegs); bid /= p.n_ysegs;
-  const int t = (int)(bid % p.n_thr); bid /= p.n_thr;
-  const long long plane = bid;
-  const ThrDev thr = p.thr.t[TM ? t : 0];
-
-  const int ya = yseg * p.seg_rows;
-  const int yb = min(p.ny, ya + p.seg_rows);
-  const int x0 = strip * p.W;
-  const bool wrap = (p.flags & NBH_WRAP_X) != 0;
-  const bool sum_only = (p.flags & NBH_SUM_ONLY) != 0;
-
-  // this thread's VEC columns
-  const int c0 = threadIdx.x * VEC;             // strip-local
-  int gx = x0 - p.hl + c0;                      // global (may be out of range)
-  bool col_active = (gx >= 0) && (gx < p.nx);
-  if (wrap) {
-    gx %= p.nx; if (gx < 0) gx += p.nx;
-    col_active = true;
-  }
-
-  for (int k = threadIdx.x + 1; k <= nb; k += TX) rtab[k] = 1.0 / (double)k;
-  for (int s = 0; s < nb; ++s) {
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      ring[s * WS + c0 + v] = 0.f;
-      if (MASKND) cring[s * WS + c0 + v] = 0.f;
-    }
-  }
-  __syncthreads();
-
-  double V[VEC];
-  float CV[VEC];
-#pragma unroll
-  for (int v = 0; v < VEC; ++v) { V[v] = 0.0; CV[v] = 0.f; }
-
-  // quirk detection state (only needed when a mean is produced)
-  unsigned long long ne_col = 0, ne_top = 0, ne_bot = 0;
-  float nanacc = 0.f;
-
-  const float* in_plane = p.in + plane * p.plane_stride;
-  const uint8_t* mnd_plane = MASKND ? p.mask_nd + plane * p.plane_stride : nullptr;
-  const int R = p.n_members;
-
-  int slot = 0;
-  int brow = 0;
-  int batch_y0 = ya;
-  for (int yy = ya - r; yy < yb + r; ++yy) {
-    float P[VEC];
-    float PC[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) { P[v] = 0.f; PC[v] = 0.f; }
-    const bool row_in = (yy >= 0) && (yy < p.ny);
-    if (row_in && col_active) {
-      const long long off = (long long)yy * p.nx + gx;
-      uint8_t m2[VEC];
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) m2[v] = 1;
-      if (p.mask2d) VecLoad<VEC>::ldm(p.mask2d + off, m2);
-      unsigned long long ne_row = 0;
-      constexpr int MB = 9;                  // member loads kept in flight together
-      for (int mb = 0; mb < R; mb += MB) {
-        float d[MB][VEC];
-#pragma unroll
-        for (int j = 0; j < MB; ++j) {
-          if (mb + j < R) VecLoad<VEC>::ld(in_plane + (long long)(mb + j) * p.member_stride + off, d[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < MB; ++j) {
-          if (mb + j < R) {
-            uint8_t mn[VEC];
-            if (MASKND) VecLoad<VEC>::ldm(mnd_plane + off, mn);
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-              bool valid = m2[v] != 0;
-              bool seen = true;
-              if (MASKND) { seen = mn[v] == 0; valid = valid && seen; }
-              if (seen) nanacc = max_nan(nanacc, fabsf(d[j][v]));
-              float tv = TM ? truth_value(d[j][v], thr) : d[j][v];
-              tv = valid ? tv : 0.f;
-              P[v] += tv;
-              if (MASKND) PC[v] = valid ? 1.f : 0.f;
-              if (tv != 1.0f) ne_row |= 1ull << (mb + j);
-            }
-          }
-        }
-      }
-      ne_col |= ne_row;
-      if (yy <= r) ne_top |= ne_row;
-      if (yy >= p.ny - 1 - r) ne_bot |= ne_row;
-    }
-    // vertical running sums through the ring (thread-private columns)
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      const int ri = slot * WS + c0 + v;
-      const float old = ring[ri];
-      ring[ri] = P[v];
-      V[v] += (double)P[v] - (double)old;
-      if (MASKND) {
-        const float oc = cring[ri];
-        cring[ri] = PC[v];
-        CV[v] += PC[v] - oc;
-      }
-    }
-    slot = (slot + 1 == nb) ? 0 : slot + 1;
-
-    const int y = yy - r;                       // output row completed by this input row
-    if (y >= ya) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        vbuf[brow * WSP + pidx(c0 + v, CPS)] = V[v];
-        if (MASKND) cbuf[brow * WSP + pidx(c0 + v, CPS)] = CV[v];
-      }
-      ++brow;
-      if (brow == nwarps || y == yb - 1) {
-        __syncthreads();
-        if (warp < brow) {
-          // ---- horizontal pass: one warp per output row ----
-          const int yo = batch_y0 + warp;
-          double* row = vbuf + warp * WSP;
-          float* crow = cbuf + warp * WSP;
-          // lane-local inclusive prefix over CPL contiguous columns
-          const int base = lane * CPL + lane;   // pidx(lane*CPL)
-          double acc = 0.0;
-          float cacc = 0.f;
-          for (int j = 0; j < CPL; ++j) {
-            acc += row[base + j];
-            row[base + j] = acc;
-            if (MASKND) { cacc += crow[base + j]; crow[base + j] = cacc; }
-          }
-          // exclusive scan of lane totals
-          double incl = acc;
-          float cincl = cacc;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            double o = __shfl_up_sync(0xffffffffu, incl, d);
-            float oc = __shfl_up_sync(0xffffffffu, cincl, d);
-            if (lane >= d) { incl += o; cincl += oc; }
-          }
-          const double lane_off = incl - acc;
-          const float clane_off = cincl - cacc;
-          for (int j = 0; j < CPL; ++j) {
-            row[base + j] += lane_off;
-            if (MASKND) crow[base + j] += clane_off;
-          }
-          __syncwarp();
-          // rows/cols of the window inside the domain (zero padding: nbhood.py:395-397)
-          const int rows_in = min(yo + r, p.ny - 1) - max(yo - r, 0) + 1;
-          const double rrow = rtab[rows_in] * p.inv_members;
-          const long long obase = ((plane * p.n_thr + t) * p.ny + yo) * (long long)p.nx;
-          for (int c = p.hl + lane * VEC; c < p.hl + p.W; c += 32 * VEC) {
-            const int xg = x0 + (c - p.hl);
-            if (xg >= p.nx) break;
-            float o[VEC];
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-              const int cc = c + v;
-              const int xo = xg + v;
-              const int hi = cc + r, lo = cc - r - 1;
-              double S = row[pidx(hi, CPS)] - (lo >= 0 ? row[pidx(lo, CPS)] : 0.0);
-              if (MASKND) {
-                float C = crow[pidx(hi, CPS)] - (lo >= 0 ? crow[pidx(lo, CPS)] : 0.f);
-                o[v] = sum_only ? (float)S
-                                : (C == 0.f ? __int_as_float(0x7fc00000) : (float)(S / (double)C));
-              } else if (sum_only) {
-                o[v] = (float)(S * p.inv_members);
-              } else if (p.mask2d) {
-                o[v] = (float)(S * p.rcp_count[(long long)yo * p.nx + xo] * p.inv_members);
-              } else {
-                const int cols_in = wrap ? nb : (min(xo + r, p.nx - 1) - max(xo - r, 0) + 1);
-                o[v] = (float)(S * rrow * rtab[cols_in]);
-              }
-            }
-            VecLoad<VEC>::st(p.out + obase + xg, o);
-            if (p.out_mask) {
-#pragma unroll
-              for (int v = 0; v < VEC; ++v) {
-                const long long pt = (long long)yo * p.nx + xg + v;
-                bool masked = p.mask2d ? (p.mask2d[pt] == 0) : false;
-                if (MASKND) masked = masked || (mnd_plane[pt] != 0);
-                p.out_mask[obase + xg + v] = masked ? 1 : 0;
-              }
-            }
-          }
-        }
-        __syncthreads();
-        batch_y0 += brow;
-        brow = 0;
-      }
-    }
-  }
-
-  // ---- epilogue: NaN flag and edge-band flags for the trimming fix-up ----
-  if (__isnanf(nanacc)) atomicOr(reinterpret_cast<unsigned*>(p.status), 1u);
-  if (!sum_only) {
-    // only VEC groups fully inside the bands count (under-approximation => conservative)
-    const bool in_dom = col_active && !wrap && (x0 - p.hl + c0 >= 0);
-    const int gx_raw = x0 - p.hl + c0;
-    const bool left = in_dom && (gx_raw + VEC - 1 <= r);
-    const bool right = in_dom && (gx_raw >= p.nx - 1 - r) && (gx_raw + VEC - 1 < p.nx);
-    unsigned long long f_left = left ? ne_col : 0ull, f_right = right ? ne_col : 0ull;
-    if (wrap) { f_left = ne_col; f_right = ne_col; }
-    unsigned long long masks[4] = {ne_top, ne_bot, f_left, f_right};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      unsigned lo32 = __reduce_or_sync(0xffffffffu, (unsigned)masks[k]);
-      unsigned hi32 = __reduce_or_sync(0xffffffffu, (unsigned)(masks[k] >> 32));
-      masks[k] = ((unsigned long long)hi32 << 32) | lo32;
-    }
-    if (lane == 0) {
-      for (int m = 0; m < R; ++m) {
-        unsigned bits = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) bits |= (unsigned)((masks[k] >> m) & 1ull) << k;
-        if (bits) atomicOr(p.edge_flags + ((plane * R + m) * p.n_thr + t), bits);
-      }
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------
 // Trimming fix-up (improver/nbhood/nbhood.py:341-409).  The reference trims
@@ -306,6 +26,14 @@ square_kernel(const SqParams p) {
 // for those (rare) slices the exact bounding boxes and min/max are built here
 // and the affected frame points are recomputed.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ int float_key(float f) {
+  int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) {
+  return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
+}
+
 template <int TM>
 __device__ __forceinline__ float load_value(const SqParams& p, long long plane, int m, const ThrDev& thr,
                                             long long pt, bool* valid, bool* seen, float* raw_tv) {
@@ -424,10 +152,10 @@ square_fixup_kernel(const SqParams p, int chunks) {
   }
 }
 
-__global__ void init_stats_kernel(unsigned* flags, SliceStats* stats, long long n, int sum_only) {
+__global__ void init_stats_kernel(unsigned* flags, SliceStats* stats, long long n, unsigned init_bits) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  flags[i] = sum_only ? 0xFu : 0u;
+  flags[i] = init_bits;
   SliceStats s;
   s.y0min = s.x0min = s.y1min = s.x1min = INT_MAX;
   s.y0max = s.x0max = s.y1max = s.x1max = -1;
@@ -464,11 +192,6 @@ __global__ void count_cols_kernel(const uint16_t* tmp, double* rcp, int ny, int 
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
-struct SqPlan {
-  int vec, tx, WS, hl, W, n_strips, n_ysegs, seg_rows;
-  size_t smem;
-};
-
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static size_t sq_smem_bytes(int tx, int vec, int nb, bool masknd) {
@@ -483,70 +206,99 @@ int env_int(const char* name, int dflt) {
   return s && *s ? atoi(s) : dflt;
 }
 
+// Choose the strip width (threads per block), the y segmentation and the load
+// grouping.  Cost model: issue slots wasted on idle lanes, halo rows re-read
+// from HBM by every y segment, and the partially filled last wave.
 static int plan_square(const NbhDesc& d, bool masknd, SqPlan* pl) {
   const int r = d.cells, nb = 2 * r + 1;
   int vec = (d.nx % 4 == 0) ? 4 : (d.nx % 2 == 0 ? 2 : 1);
+  if (r < 3) vec = min(vec, 2);          // edge-band flags need whole VEC groups inside r+1 columns
+  if (r < 1) vec = 1;
   vec = min(vec, env_int("NBH_SQ_VEC", 4));
-  int dev = 0;
+  int dev = 0, smem_max = 0;
   cudaGetDevice(&dev);
-  int smem_max = 0;
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (smem_max <= 0) smem_max = 227 * 1024;
-  int tx = env_int("NBH_SQ_TX", 128);
-  for (;; ) {
-    // widen the strip until the halo is at most ~1/3 of it, shrink to fit smem
-    while (tx < 256 && tx * vec < 6 * r) tx += 32;
-    while (tx > 32 && sq_smem_bytes(tx, vec, nb, masknd) > (size_t)smem_max) tx -= 32;
-    if (sq_smem_bytes(tx, vec, nb, masknd) <= (size_t)smem_max && tx * vec > 2 * r + 2 * vec) break;
-    if (vec > 1) { vec /= 2; tx = 128; continue; }
+  const int forced_tx = env_int("NBH_SQ_TX", 0);
+  const int forced_ysegs = env_int("NBH_SQ_YSEGS", 0);
+  const long long units = d.n_planes * (long long)max(d.n_thresholds, 1);
+  double best_cost = 1e30;
+  bool found = false;
+  for (;;) {
+    for (int tx = 64; tx <= kSqMaxThreads; tx += 32) {
+      if (forced_tx && tx != forced_tx) continue;
+      const size_t smem = sq_smem_bytes(tx, vec, nb, masknd);
+      if (smem > (size_t)smem_max) continue;
+      const int WS = tx * vec;
+      const int hl = (r + vec - 1) / vec * vec;
+      const int wmax = (WS - hl - r) / vec * vec;
+      if (wmax < vec) continue;
+      const int n_strips = (d.nx + wmax - 1) / wmax;
+      int W = ((d.nx + n_strips - 1) / n_strips + vec - 1) / vec * vec;
+      W = min(W, wmax);
+      const double lane_eff = (double)d.nx / ((double)n_strips * WS);
+      int per_sm = min(16, min((int)(65536 / (tx * 170)), (int)((size_t)smem_max / (smem + 1024))));
+      per_sm = max(per_sm, 1);
+      const double slots = (double)sm_count() * per_sm;
+      for (int ysegs = 1; ysegs <= 64; ++ysegs) {
+        if (forced_ysegs && ysegs != forced_ysegs) continue;
+        const int seg_rows = (d.ny + ysegs - 1) / ysegs;
+        if (ysegs > 1 && seg_rows < 4 * r) break;
+        const int n_ysegs = (d.ny + seg_rows - 1) / seg_rows;
+        if (n_ysegs != ysegs) continue;
+        const double blocks = (double)units * n_strips * n_ysegs;
+        const double waves = blocks / slots;
+        const double tail = ceil(waves) / waves;
+        const double halo = 1.0 + (n_ysegs > 1 ? 2.0 * r / seg_rows : 0.0);
+        // idle lanes only cost issue slots; weigh them less than HBM re-reads
+        const double cost = tail * halo * (1.0 + 0.5 * (1.0 / lane_eff - 1.0)) *
+                            (1.0 + 0.25 * (double)(hl + r) / W);
+        if (cost < best_cost) {
+          best_cost = cost; found = true;
+          pl->vec = vec; pl->tx = tx; pl->WS = WS; pl->hl = hl; pl->W = W; pl->n_strips = n_strips;
+          pl->n_ysegs = n_ysegs; pl->seg_rows = seg_rows; pl->smem = smem;
+        }
+      }
+    }
+    if (found) break;
+    if (vec > 1) { vec /= 2; continue; }
     set_error("square neighbourhood radius of %d cells does not fit in shared memory", r);
     return 1;
   }
-  pl->vec = vec; pl->tx = tx; pl->WS = tx * vec;
-  pl->hl = (r + vec - 1) / vec * vec;
-  int wmax = (pl->WS - pl->hl - r) / vec * vec;
-  pl->n_strips = (d.nx + wmax - 1) / wmax;
-  // balance strips, keep W a multiple of VEC
-  int w = (d.nx + pl->n_strips - 1) / pl->n_strips;
-  w = (w + vec - 1) / vec * vec;
-  pl->W = min(w, wmax);
-  const long long tiles_xy = (long long)pl->n_strips * d.n_planes * max(d.n_thresholds, 1);
-  int ysegs = env_int("NBH_SQ_YSEGS", 0);
+  const int mbm = vec == 4 ? 9 : 18;
+  if (masknd || d.n_members == 1) { pl->mode = SQ_ROWS; pl->mb = vec == 4 ? 4 : 8; }
+  else if (d.n_members == mbm) { pl->mode = SQ_MEMBERS_FULL; pl->mb = mbm; }
+  else if (d.n_members < mbm) { pl->mode = SQ_MEMBERS_PART; pl->mb = mbm; }
+  else { pl->mode = SQ_CURSOR; pl->mb = mbm; }
+  return 0;
+}
+
+// Geometry of the warp-autonomous kernel; returns false when the radius is
+// too large for a 32*VEC-column strip (the block-cooperative kernel is used).
+static bool plan_square_warp(const NbhDesc& d, int vec, SqWarpGeom* g) {
+  const int r = d.cells;
+  const bool wrap = (d.flags & NBH_WRAP_X) != 0;
+  g->WS = 32 * vec;
+  g->hl = (r + vec - 1) / vec * vec;
+  g->W = (g->WS - g->hl - r) / vec * vec;
+  g->W0 = wrap ? g->W : (g->WS - r) / vec * vec;
+  if (g->W < (g->WS * 6) / 10) return false;
+  if (sq_warp_smem_bytes(vec, 2 * r + 1) > 200 * 1024) return false;
+  g->n_strips = wrap ? (d.nx + g->W - 1) / g->W
+                     : 1 + (d.nx > g->W0 ? (d.nx - g->W0 + g->W - 1) / g->W : 0);
+  const long long units = d.n_planes * (long long)max(d.n_thresholds, 1) * g->n_strips;
+  int ysegs = env_int("NBH_SQW_YSEGS", 0);
   if (ysegs <= 0) {
-    // enough blocks for ~4 waves of 148 SMs x resident blocks, segments no shorter than 8 halos
-    const long long want = 4LL * sm_count() * 3;
-    ysegs = (int)max(1LL, min((long long)d.ny / max(16, 8 * r), (want + tiles_xy - 1) / tiles_xy));
+    // ~4 tasks per resident warp slot, segments of at least max(48, 8r) rows
+    const long long slots = (long long)sm_count() * 12;
+    const int max_segs = max(1, d.ny / max(48, 8 * r));
+    ysegs = (int)min((long long)max_segs, max(1LL, (4 * slots + units - 1) / units));
   }
   ysegs = max(1, min(ysegs, d.ny));
-  pl->seg_rows = (d.ny + ysegs - 1) / ysegs;
-  pl->n_ysegs = (d.ny + pl->seg_rows - 1) / pl->seg_rows;
-  pl->smem = sq_smem_bytes(tx, vec, nb, masknd);
-  return 0;
-}
-
-template <int VEC, int TM, bool MASKND>
-static int launch_square_t(const SqParams& p, const SqPlan& pl, long long blocks, cudaStream_t st) {
-  auto kern = square_kernel<VEC, TM, MASKND>;
-  NBH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-  kern<<<(unsigned)blocks, pl.tx, pl.smem, st>>>(p);
-  NBH_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-template <int VEC, int TM>
-static int launch_square_m(const SqParams& p, const SqPlan& pl, long long blocks, bool masknd, cudaStream_t st) {
-  return masknd ? launch_square_t<VEC, TM, true>(p, pl, blocks, st)
-                : launch_square_t<VEC, TM, false>(p, pl, blocks, st);
-}
-
-template <int VEC>
-static int launch_square_v(const SqParams& p, const SqPlan& pl, long long blocks, int tm, bool masknd,
-                           cudaStream_t st) {
-  switch (tm) {
-    case 0: return launch_square_m<VEC, 0>(p, pl, blocks, masknd, st);
-    case 1: return launch_square_m<VEC, 1>(p, pl, blocks, masknd, st);
-    default: return launch_square_m<VEC, 2>(p, pl, blocks, masknd, st);
-  }
+  g->seg_rows = (d.ny + ysegs - 1) / ysegs;
+  g->n_ysegs = (d.ny + g->seg_rows - 1) / g->seg_rows;
+  g->n_tasks = units * g->n_ysegs;
+  return true;
 }
 
 struct SqWorkspace {
@@ -625,14 +377,17 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   p.W = pl.W; p.WS = pl.WS; p.hl = pl.hl; p.n_strips = pl.n_strips; p.n_ysegs = pl.n_ysegs;
   p.seg_rows = pl.seg_rows;
   p.n_thr = max(d->n_thresholds, 1);
+  p.cpl = pl.WS / 32;
+  p.cpl_magic = (65536 + p.cpl - 1) / p.cpl;
   p.inv_members = 1.0 / (double)d->n_members;
   if (d->flags & NBH_SUM_ONLY) p.inv_members = 1.0;   // a sum is never averaged
 
   const long long nslices = d->n_planes * d->n_members * p.n_thr;
   const bool sum_only = (d->flags & NBH_SUM_ONLY) != 0;
   NBH_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int32_t), st));
+  const unsigned init_bits = sum_only ? 0xFu : ((d->flags & NBH_WRAP_X) ? 0xCu : 0u);
   init_stats_kernel<<<(unsigned)((nslices + 255) / 256), 256, 0, st>>>(w.edge_flags, w.stats, nslices,
-                                                                    sum_only ? 1 : 0);
+                                                                    init_bits);
   if (d->mask2d && !masknd && !sum_only) {
     const long long n = (long long)d->ny * d->nx;
     count_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d->mask2d, w.tmp, d->ny, d->nx,
@@ -643,12 +398,23 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   const long long blocks = (long long)pl.n_strips * pl.n_ysegs * p.n_thr * d->n_planes;
   NBH_REQUIRE(blocks < (1LL << 31), "too many blocks (%lld); split the launch", blocks);
   int rc;
-  {
+  SqWarpGeom wg;
+  const bool use_warp = !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && plan_square_warp(*d, pl.vec, &wg);
+  if (use_warp) {
     ProfileScope prof(st);
+    const bool m2d = d->mask2d != nullptr;
     switch (pl.vec) {
-      case 4: rc = launch_square_v<4>(p, pl, blocks, tm, masknd, st); break;
-      case 2: rc = launch_square_v<2>(p, pl, blocks, tm, masknd, st); break;
-      default: rc = launch_square_v<1>(p, pl, blocks, tm, masknd, st); break;
+      case 4: rc = launch_square_warp_vec<4>(p, wg, tm, m2d, st); break;
+      case 2: rc = launch_square_warp_vec<2>(p, wg, tm, m2d, st); break;
+      default: rc = launch_square_warp_vec<1>(p, wg, tm, m2d, st); break;
+    }
+  } else {
+    ProfileScope prof(st);
+    const bool m2d = d->mask2d != nullptr;
+    switch (pl.vec) {
+      case 4: rc = launch_square_vec<4>(p, pl, blocks, tm, masknd, m2d, st); break;
+      case 2: rc = launch_square_vec<2>(p, pl, blocks, tm, masknd, m2d, st); break;
+      default: rc = launch_square_vec<1>(p, pl, blocks, tm, masknd, m2d, st); break;
     }
   }
   if (rc) return rc;

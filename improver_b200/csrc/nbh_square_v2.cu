@@ -1,0 +1,6 @@
+// Instantiations of the square neighbourhood kernel for 2-wide vector loads.
+#include "nbh_square.cuh"
+
+namespace nbh {
+NBH_DEFINE_SQUARE_VEC(2)
+}  // namespace nbh

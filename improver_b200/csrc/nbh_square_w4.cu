@@ -1,0 +1,6 @@
+// Instantiations of the warp-autonomous square kernel for 4-wide vector loads.
+#include "nbh_square_warp.cuh"
+
+namespace nbh {
+NBH_DEFINE_SQUARE_WARP_VEC(4)
+}  // namespace nbh
