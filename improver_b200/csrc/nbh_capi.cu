@@ -31,6 +31,78 @@ ProfileScope::~ProfileScope() {
   g_prof_valid = true;
 }
 
+// Host restatement of the device truth value (same float32 operation order)
+static float host_truth(const ThrDev& p, float d) {
+  if (p.mode == 1) {
+    bool b;
+    switch (p.op) {
+      case NBH_OP_GT: b = d > p.thr; break;
+      case NBH_OP_GE: b = d >= p.thr; break;
+      case NBH_OP_LT: b = d < p.thr; break;
+      default: b = d <= p.thr; break;
+    }
+    return b ? 1.f : 0.f;
+  }
+  if (p.mode == 3) {
+    const bool below = d < p.thr;
+    const double a = below ? ((double)d - p.lo64) : (double)(d - p.thr);
+    const double den = below ? (double)p.den_lo : (double)p.den_hi;
+    const double off = below ? 0.0 : 0.5;
+    double v = a * 0.5 / den + off;
+    v = std::fmin(std::fmax(v, off), off + 0.5);
+    if (p.op >= NBH_OP_LT) v = 1.0 - v;
+    return (float)v;
+  }
+  const float dc = std::fmin(std::fmax(d, p.lo), p.hi);
+  const bool below = d < p.thr;
+  const float base = below ? p.lo : p.thr;
+  const float den2 = below ? p.den2_lo : p.den2_hi;
+  const float rcph = below ? p.rcph_lo : p.rcph_hi;
+  const float off = below ? 0.f : 0.5f;
+  const float a = dc - base;
+  const float q0 = a * rcph;
+  const float rem = std::fmaf(-den2, q0, a);
+  float v = std::fmaf(rem, rcph, q0) + off;
+  if (p.op >= NBH_OP_LT) v = 1.0f - v;
+  return v;
+}
+
+static uint32_t f2ord(float f) {
+  uint32_t b; memcpy(&b, &f, 4);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+static float ord2f(uint32_t k) {
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  float f; memcpy(&f, &b, 4);
+  return f;
+}
+
+// [one_lo, one_hi]: the interval of data values whose truth value is exactly 1
+// (the membership function is monotone, so the set is an interval ending at +-inf).
+static void find_one_interval(ThrDev* d) {
+  const float inf = INFINITY;
+  const bool decreasing = (d->mode != 1) ? (d->op >= NBH_OP_LT) : (d->op >= NBH_OP_LT);
+  // search over the total order of floats between -inf and +inf
+  uint32_t lo = f2ord(-inf), hi = f2ord(inf);
+  if (!decreasing) {
+    // smallest d with truth == 1
+    if (host_truth(*d, inf) != 1.f) { d->one_lo = inf; d->one_hi = -inf; return; }
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      if (host_truth(*d, ord2f(mid)) == 1.f) hi = mid; else lo = mid + 1;
+    }
+    d->one_lo = ord2f(lo); d->one_hi = inf;
+  } else {
+    // largest d with truth == 1
+    if (host_truth(*d, -inf) != 1.f) { d->one_lo = inf; d->one_hi = -inf; return; }
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo + 1) / 2;
+      if (host_truth(*d, ord2f(mid)) == 1.f) lo = mid; else hi = mid - 1;
+    }
+    d->one_lo = -inf; d->one_hi = ord2f(lo);
+  }
+}
+
 // Host preparation of one threshold, mirroring the dtype handling of
 // improver/threshold.py:434 (threshold cast to the float32 data dtype) and
 // numpy's weak-scalar promotion of the python-float fuzzy bounds.
@@ -41,6 +113,7 @@ int make_thr_dev(const NbhThreshold& h, ThrDev* d, bool ma_arith) {
   d->thr = (float)h.value;
   if (h.lo == h.hi) {           // threshold.py:438-439
     d->mode = 1;
+    find_one_interval(d);
     return 0;
   }
   NBH_REQUIRE(h.lo <= h.value && h.value <= h.hi, "Threshold must be within bounds: !( %g <= %g <= %g )",
@@ -58,6 +131,15 @@ int make_thr_dev(const NbhThreshold& h, ThrDev* d, bool ma_arith) {
   d->den2_hi = 2.0f * d->den_hi;
   d->rcph_lo = (float)(0.5 / (double)d->den_lo);
   d->rcph_hi = (float)(0.5 / (double)d->den_hi);
+  // convex (slope below thr smaller than above) -> max of the two lines; concave -> min
+  const float sigma = (d->rcph_lo <= d->rcph_hi) ? 1.0f : -1.0f;
+  d->fs_lo = sigma * d->rcph_lo;
+  d->fs_hi = sigma * d->rcph_hi;
+  d->fc_hi = sigma * 0.5f;
+  const bool invert = h.op >= NBH_OP_LT;
+  d->f_mul = invert ? -sigma : sigma;
+  d->f_add = invert ? 1.0f : 0.0f;
+  find_one_interval(d);
   return 0;
 }
 

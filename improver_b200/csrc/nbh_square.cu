@@ -278,21 +278,44 @@ static int plan_square(const NbhDesc& d, bool masknd, SqPlan* pl) {
 static bool plan_square_warp(const NbhDesc& d, int vec, SqWarpGeom* g) {
   const int r = d.cells;
   const bool wrap = (d.flags & NBH_WRAP_X) != 0;
-  g->WS = 32 * vec;
-  g->hl = (r + vec - 1) / vec * vec;
-  g->W = (g->WS - g->hl - r) / vec * vec;
-  g->W0 = wrap ? g->W : (g->WS - r) / vec * vec;
-  if (g->W < (g->WS * 6) / 10) return false;
-  if (sq_warp_smem_bytes(vec, 2 * r + 1) > 200 * 1024) return false;
-  g->n_strips = wrap ? (d.nx + g->W - 1) / g->W
-                     : 1 + (d.nx > g->W0 ? (d.nx - g->W0 + g->W - 1) / g->W : 0);
+  // one or two VEC groups per lane: pick the strip width with the fewest idle lanes
+  double best = 0.0;
+  int forced = env_int("NBH_SQW_GROUPS", 0);
+  for (int groups = 1; groups <= (vec < 4 ? 2 : 1); ++groups) {
+    if (forced && groups != forced) continue;
+    const int WS = 32 * vec * groups;
+    const int hl = (r + vec - 1) / vec * vec;
+    const int W = (WS - hl - r) / vec * vec;
+    const int W0 = wrap ? W : (WS - r) / vec * vec;
+    if (W < (WS * 6) / 10) continue;
+    if (sq_warp_smem_bytes(vec, groups, 2 * r + 1) * 3 > 200 * 1024) continue;
+    const int n_strips = wrap ? (d.nx + W - 1) / W : 1 + (d.nx > W0 ? (d.nx - W0 + W - 1) / W : 0);
+    const double eff = (double)d.nx / ((double)n_strips * WS);
+    if (eff > best + 0.02) {
+      best = eff;
+      g->WS = WS; g->hl = hl; g->W = W; g->W0 = W0; g->n_strips = n_strips;
+    }
+  }
+  if (best == 0.0) return false;
   const long long units = d.n_planes * (long long)max(d.n_thresholds, 1) * g->n_strips;
   int ysegs = env_int("NBH_SQW_YSEGS", 0);
   if (ysegs <= 0) {
-    // ~4 tasks per resident warp slot, segments of at least max(48, 8r) rows
-    const long long slots = (long long)sm_count() * 12;
-    const int max_segs = max(1, d.ny / max(48, 8 * r));
-    ysegs = (int)min((long long)max_segs, max(1LL, (4 * slots + units - 1) / units));
+    // Every y segment re-reads 2r halo rows (mostly from L2) and the last,
+    // partially filled wave of warp tasks idles part of the machine: pick the
+    // segmentation minimising halo x tail.
+    const double slots = (double)sm_count() * 12;
+    double best_cost = 1e30;
+    ysegs = 1;
+    for (int cand = 1; cand <= 64; ++cand) {
+      const int seg_rows = (d.ny + cand - 1) / cand;
+      if (cand > 1 && seg_rows < max(32, 6 * r)) break;
+      if ((d.ny + seg_rows - 1) / seg_rows != cand) continue;
+      const double waves = (double)units * cand / slots;
+      const double tail = ceil(waves) / waves;
+      const double halo = 1.0 + 2.0 * r / seg_rows;
+      const double cost = tail * halo;
+      if (cost < best_cost) { best_cost = cost; ysegs = cand; }
+    }
   }
   ysegs = max(1, min(ysegs, d.ny));
   g->seg_rows = (d.ny + ysegs - 1) / ysegs;
@@ -343,6 +366,7 @@ int validate_desc(const NbhDesc* d) {
 int fill_thresholds(const NbhDesc& d, ThrSet* ts, int* tm) {
   ts->n = d.n_thresholds;
   *tm = 0;
+  ts->t[0].one_lo = ts->t[0].one_hi = 1.0f;      // raw data: "is one" <=> d == 1
   for (int i = 0; i < d.n_thresholds; ++i) {
     if (make_thr_dev(d.thresholds[i], &ts->t[i], d.mask_nd != nullptr)) return 1;
     const int m = ts->t[i].mode == 3 ? 2 : ts->t[i].mode;

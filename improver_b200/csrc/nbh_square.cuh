@@ -261,38 +261,17 @@ square_kernel(const __grid_constant__ SqParams p) {
     }
   };
 
-  // Edge-band bookkeeping for the trimming fix-up.  Only rows within r+1 of
-  // the top/bottom edge and the few threads owning columns within r+1 of the
-  // left/right edge ever run it; it re-reads the row (L1/L2 hit) in a rolled
-  // loop so that the streaming loop stays free of this logic.
-  auto flag_pass = [&](int yy) {
-    if (sum_only || !col_active || yy < 0 || yy >= p.ny) return;
-    const bool top = yy <= r, bot = yy >= p.ny - 1 - r;
-    if (!(colband || top || bot)) return;
-    const long long off = (long long)yy * p.nx;
-    unsigned m2 = 0x01010101u;
-    if (M2D) m2 = ldm_packed<VEC>(m2_col + off);
-    unsigned long long ne = 0;
-    const float* q = in_col + off;
-#pragma unroll 1
-    for (int m = 0; m < R; ++m, q += mstride) {
-      float d[VEC];
-      VecLoad<VEC>::ld(q, d);
-      unsigned mnd = 0;
-      if (MASKND) mnd = ldm_packed<VEC>(mnd_col + off);
-      bool any = false;
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        bool valid = ((m2 >> (8 * v)) & 0xffu) != 0;
-        if (MASKND) valid = valid && (((mnd >> (8 * v)) & 0xffu) == 0);
-        const float tv = valid ? truth_value_t<TM>(d[v], thr) : 0.f;
-        any = any || (tv != 1.0f);
-      }
-      if (any) ne |= 1ull << m;
-    }
-    ne_col |= ne;
-    if (top) ne_top |= ne;
-    if (bot) ne_bot |= ne;
+  // Edge-band bookkeeping for the trimming fix-up: warps that own columns in
+  // the left / right band, and all warps on rows within r+1 of the top /
+  // bottom edge, run the flagged copy of the accumulate loop.
+  const bool warp_band = __any_sync(0xffffffffu, colband);
+  unsigned long long ne_row = 0;
+  auto row_flags_done = [&](int yy) {
+    if (sum_only) return;
+    if (colband) ne_col |= ne_row;
+    if (yy <= r) ne_top |= ne_row;
+    if (yy >= p.ny - 1 - r) ne_bot |= ne_row;
+    ne_row = 0;
   };
 
   auto issue = [&](float (&buf)[MB][VEC], unsigned (&mk)[MKN], unsigned (&mn)[MKN]) {
@@ -353,27 +332,36 @@ square_kernel(const __grid_constant__ SqParams p) {
         if (act) {
           if (M2D && (kMembers ? j == 0 : m == 0)) cur_m2 = mk[kMembers ? 0 : j];
           const unsigned mnd = MASKND ? mn[kMembers ? 0 : j] : 0u;
+          auto body = [&](bool flagged) {
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) {
-            const float d = buf[j][v];
-            bool valid = true, seen = true;
-            if (M2D) valid = ((cur_m2 >> (8 * v)) & 0xffu) != 0;
-            if (MASKND) { seen = ((mnd >> (8 * v)) & 0xffu) == 0; valid = valid && seen; }
-            if (MASKND) { if (seen) nanacc = max_nan(nanacc, fabsf(d)); }
-            else nanacc = max_nan(nanacc, fabsf(d));
-            float tv = truth_value_t<TM>(d, thr);
-            if (M2D || MASKND) tv = valid ? tv : 0.f;
-            P[v] += tv;
-            if (MASKND) PC[v] = valid ? 1.f : 0.f;
-          }
+            for (int v = 0; v < VEC; ++v) {
+              const float d = buf[j][v];
+              bool valid = true, seen = true;
+              if (M2D) valid = ((cur_m2 >> (8 * v)) & 0xffu) != 0;
+              if (MASKND) { seen = ((mnd >> (8 * v)) & 0xffu) == 0; valid = valid && seen; }
+              if (MASKND) { if (seen) nanacc = max_nan(nanacc, fabsf(d)); }
+              else nanacc = max_nan(nanacc, fabsf(d));
+              float tv = truth_value_sum<TM>(d, thr);
+              if (M2D || MASKND) tv = valid ? tv : 0.f;
+              P[v] += tv;
+              if (MASKND) PC[v] = valid ? 1.f : 0.f;
+              if (flagged) { if (!valid || truth_not_one(d, thr)) ne_row |= 1ull << m; }
+            }
+          };
+          if (!sum_only && (warp_band || yy <= r || yy >= p.ny - 1 - r)) body(true); else body(false);
         }
         if (MODE == SQ_ROWS || MODE == SQ_CURSOR) {
-          if (m == R - 1) { flag_pass(yy); finish_row(yy); }
+          if (m == R - 1) { if (act) row_flags_done(yy); finish_row(yy); }
         }
       }
       if (MODE == SQ_CURSOR) { if (++cm == R) { cm = 0; ++cy; } }
     }
-    if (kMembers) { if (cy < yend) { flag_pass(cy); finish_row(cy); } }
+    if (kMembers) {
+      if (cy < yend) {
+        if (col_active && cy >= 0 && cy < p.ny) row_flags_done(cy);
+        finish_row(cy);
+      }
+    }
     if (MODE == SQ_ROWS) cy += MB;
     else if (kMembers) cy += 1;
   };

@@ -21,14 +21,14 @@ namespace nbh {
 constexpr int kSqWarpsPerBlock = 4;
 
 struct SqWarpGeom {
-  int WS;        // columns loaded per warp (32 * VEC)
+  int WS;        // columns loaded per warp (32 * VEC * groups)
   int W0, W;     // output columns of strip 0 / of the other strips
   int hl;        // left halo of strips > 0 (multiple of VEC, >= r)
   int n_strips, n_ysegs, seg_rows;
   long long n_tasks;
 };
 
-template <int VEC, int TM, bool M2D, bool ROWS, bool FULL, int MB>
+template <int VEC, int G, int TM, bool M2D, bool ROWS, bool FULL, int MB>
 __global__ void __launch_bounds__(kSqWarpsPerBlock * 32, 3)
 square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -70,139 +70,161 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
     load0 = x0 - g.hl; wk = g.W;
   }
   const int c_out0 = x0 - load0;                   // strip-local first output column
-  const int c0 = lane * VEC;
-  const int gx_raw = load0 + c0;
-  int gx = gx_raw;
-  bool col_active = (gx >= 0) && (gx < p.nx);
-  if (wrap) { gx %= p.nx; if (gx < 0) gx += p.nx; col_active = true; }
-  // with a periodic x axis there is no left / right edge (flags preset by the host)
-  const bool colband = !sum_only && !wrap && col_active &&
-                       ((gx_raw + VEC - 1 <= r) || (gx_raw >= p.nx - 1 - r && gx_raw + VEC - 1 < p.nx));
+  // lane owns G groups of VEC adjacent columns: c = g * 32 * VEC + lane * VEC + v
+  int c0[G], gxr[G], gx[G];
+  bool col_active[G], colband[G];
+  bool any_band = false;
+#pragma unroll
+  for (int g2 = 0; g2 < G; ++g2) {
+    c0[g2] = g2 * 32 * VEC + lane * VEC;
+    gxr[g2] = load0 + c0[g2];
+    gx[g2] = gxr[g2];
+    col_active[g2] = (gx[g2] >= 0) && (gx[g2] < p.nx);
+    if (wrap) { gx[g2] %= p.nx; if (gx[g2] < 0) gx[g2] += p.nx; col_active[g2] = true; }
+    // with a periodic x axis there is no left / right edge (flags preset by the host)
+    colband[g2] = !sum_only && !wrap && col_active[g2] &&
+                  ((gxr[g2] + VEC - 1 <= r) || (gxr[g2] >= p.nx - 1 - r && gxr[g2] + VEC - 1 < p.nx));
+    any_band = any_band || colband[g2];
+    if (!col_active[g2]) gx[g2] = 0;               // keep pointers in range; loads are predicated off
+  }
 
   for (int s = 0; s < nb; ++s) {
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) ring[s * WS + c0 + v] = 0.f;
+    for (int g2 = 0; g2 < G; ++g2)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) ring[s * WS + c0[g2] + v] = 0.f;
   }
   if (lane == 0) hrow[0] = 0.0;
   __syncwarp();
 
-  double V[VEC];
-  float P[VEC];
+  double V[G][VEC];
+  float P[G][VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) { V[v] = 0.0; P[v] = 0.f; }
-  unsigned long long ne_col = 0, ne_top = 0, ne_bot = 0;
+  for (int g2 = 0; g2 < G; ++g2)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { V[g2][v] = 0.0; P[g2][v] = 0.f; }
+  unsigned long long ne_left = 0, ne_right = 0, ne_top = 0, ne_bot = 0;
   float nanacc = 0.f;
-  unsigned cur_m2 = 0x01010101u;
+  unsigned cur_m2[G];
+#pragma unroll
+  for (int g2 = 0; g2 < G; ++g2) cur_m2[g2] = 0x01010101u;
   int slot = 0;
 
   const int R = p.n_members;
   const int n_chunks = ROWS ? 1 : (R + MB - 1) / MB;
   const long long mstride = p.member_stride;
   const long long row_step = (long long)dir * p.nx;
-  const float* in_col = p.in + plane * p.plane_stride + gx;
-  const uint8_t* m2_col = M2D ? p.mask2d + gx : nullptr;
+  const float* in_plane = p.in + plane * p.plane_stride;
   const long long obase0 = (plane * p.n_thr + t) * (long long)p.ny * p.nx;
 
   // issue / consume cursors: row counters k (0 .. n_rows) and member chunk index
   int ik = 0, ichunk = 0, ck = 0, cchunk = 0;
-  const float* irow = in_col + (long long)y_first * p.nx;
-  const uint8_t* irow_m2 = M2D ? m2_col + (long long)y_first * p.nx : nullptr;
+  const float* irow = in_plane + (long long)y_first * p.nx;           // row base (column 0)
+  const uint8_t* irow_m2 = M2D ? p.mask2d + (long long)y_first * p.nx : nullptr;
 
   // ---- one finished input row: ring, vertical sums, horizontal pass, store ----
   auto finish_row = [&](int k) {
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      const int ri = slot * WS + c0 + v;
-      const float old = ring[ri];
-      ring[ri] = P[v];
-      V[v] += (double)P[v] - (double)old;
-      P[v] = 0.f;
-    }
+    for (int g2 = 0; g2 < G; ++g2)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int ri = slot * WS + c0[g2] + v;
+        const float old = ring[ri];
+        ring[ri] = P[g2][v];
+        V[g2][v] += (double)P[g2][v] - (double)old;
+        P[g2][v] = 0.f;
+      }
     slot = (slot + 1 == nb) ? 0 : slot + 1;
     if (k < 2 * r) return;                               // window not complete yet
     const int yo = y_first + dir * (k - r);              // centre row of the window
-    // float64 inclusive prefix over the strip: lane-local then warp scan
-    double loc[VEC];
-    double s = 0.0;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) { s += V[v]; loc[v] = s; }
-    double incl = s;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const double o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += o;
-    }
-    const double excl = incl - s;
+    // float64 inclusive prefix over the strip: lane-local, warp scan per group, group carry
     __syncwarp();                                        // previous row's readers are done
+    double carry = 0.0;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) hrow[c0 + v + 1] = excl + loc[v];
+    for (int g2 = 0; g2 < G; ++g2) {
+      double loc[VEC];
+      double s = 0.0;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { s += V[g2][v]; loc[v] = s; }
+      double incl = s;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      const double excl = carry + incl - s;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) hrow[c0[g2] + v + 1] = excl + loc[v];
+      if (g2 + 1 < G) carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
     __syncwarp();
-    const bool is_out = (c0 >= c_out0) && (c0 < c_out0 + wk) && (gx_raw < p.nx) && col_active;
-    if (is_out) {
-      const int rows_in = min(yo + r, p.ny - 1) - max(yo - r, 0) + 1;
-      const double rrow = rtab[rows_in] * p.inv_members;
-      const long long pt0 = (long long)yo * p.nx + gx;
-      float o[VEC];
+    const int rows_in = min(yo + r, p.ny - 1) - max(yo - r, 0) + 1;
+    const double rrow = rtab[rows_in] * p.inv_members;
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const int cc = c0 + v;
-        const double S = hrow[cc + r + 1] - hrow[max(cc - r, 0)];
-        if (sum_only) {
-          o[v] = (float)S;
-        } else if (M2D) {
-          o[v] = (float)(S * p.rcp_count[pt0 + v] * p.inv_members);
-        } else {
-          const int xo = gx + v;
-          const int cols_in = wrap ? nb : (min(xo + r, p.nx - 1) - max(xo - r, 0) + 1);
-          o[v] = (float)(S * rrow * rtab[cols_in]);
+    for (int g2 = 0; g2 < G; ++g2) {
+      const bool is_out = (c0[g2] >= c_out0) && (c0[g2] < c_out0 + wk) && (gxr[g2] < p.nx) && col_active[g2];
+      if (is_out) {
+        const long long pt0 = (long long)yo * p.nx + gx[g2];
+        float o[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const int cc = c0[g2] + v;
+          const double S = hrow[cc + r + 1] - hrow[max(cc - r, 0)];
+          if (sum_only) {
+            o[v] = (float)S;
+          } else if (M2D) {
+            o[v] = (float)(S * p.rcp_count[pt0 + v] * p.inv_members);
+          } else {
+            const int xo = gx[g2] + v;
+            const int cols_in = wrap ? nb : (min(xo + r, p.nx - 1) - max(xo - r, 0) + 1);
+            o[v] = (float)(S * rrow * rtab[cols_in]);
+          }
+        }
+        VecLoad<VEC>::st(p.out + obase0 + pt0, o);
+        if (p.out_mask) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v)
+            p.out_mask[obase0 + pt0 + v] = (M2D && p.mask2d[pt0 + v] == 0) ? 1 : 0;
         }
       }
-      VecLoad<VEC>::st(p.out + obase0 + pt0, o);
-      if (p.out_mask) {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v)
-          p.out_mask[obase0 + pt0 + v] = (M2D && p.mask2d[pt0 + v] == 0) ? 1 : 0;
-      }
     }
   };
 
-  // ---- edge-band bookkeeping for the trimming fix-up (rare rows / lanes) ----
-  auto flag_pass = [&](int yy) {
-    if (sum_only || !col_active || yy < 0 || yy >= p.ny) return;
+  // ---- edge-band bookkeeping for the trimming fix-up ----
+  // A warp needs per-member "saw a value != 1" bits only while it is inside
+  // one of the four edge bands: always for the two edge strips (warp-uniform),
+  // and for rows within r+1 of the top / bottom edge.  Those chunks run the
+  // flagged copy of the accumulate loop; everything else runs the lean one.
+  const bool strip_band = __any_sync(0xffffffffu, any_band);
+  unsigned long long ne_row[G];
+#pragma unroll
+  for (int g2 = 0; g2 < G; ++g2) ne_row[g2] = 0;
+  auto row_flags_done = [&](int yy) {
+    if (sum_only) return;
     const bool top = yy <= r, bot = yy >= p.ny - 1 - r;
-    if (!(colband || top || bot)) return;
-    const long long off = (long long)yy * p.nx;
-    unsigned m2 = 0x01010101u;
-    if (M2D) m2 = ldm_packed<VEC>(m2_col + off);
-    unsigned long long ne = 0;
-    const float* q = in_col + off;
-#pragma unroll 1
-    for (int m = 0; m < R; ++m, q += mstride) {
-      float d[VEC];
-      VecLoad<VEC>::ld(q, d);
-      bool any = false;
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const bool valid = ((m2 >> (8 * v)) & 0xffu) != 0;
-        const float tv = valid ? truth_value_t<TM>(d[v], thr) : 0.f;
-        any = any || (tv != 1.0f);
-      }
-      if (any) ne |= 1ull << m;
+    for (int g2 = 0; g2 < G; ++g2) {
+      if (colband[g2] && (gxr[g2] + VEC - 1 <= r)) ne_left |= ne_row[g2];
+      if (colband[g2] && (gxr[g2] >= p.nx - 1 - r)) ne_right |= ne_row[g2];
+      if (top) ne_top |= ne_row[g2];
+      if (bot) ne_bot |= ne_row[g2];
+      ne_row[g2] = 0;
     }
-    ne_col |= ne;
-    if (top) ne_top |= ne;
-    if (bot) ne_bot |= ne;
   };
 
-  auto issue = [&](float (&buf)[MB][VEC], unsigned (&mk)[ROWS ? MB : 1]) {
+  constexpr int MKN = ROWS ? MB : 1;
+  auto issue = [&](float (&buf)[MB][G][VEC], unsigned (&mk)[MKN][G]) {
     if (ROWS) {
 #pragma unroll
       for (int j = 0; j < MB; ++j) {
         const int yy = y_first + dir * (ik + j);
-        const bool act = col_active && (ik + j < n_rows) && (yy >= 0) && (yy < p.ny);
-        if (act) {
-          VecLoad<VEC>::ld(irow, buf[j]);
-          if (M2D) mk[j] = ldm_packed<VEC>(irow_m2);
+        const bool row_ok = (ik + j < n_rows) && (yy >= 0) && (yy < p.ny);
+#pragma unroll
+        for (int g2 = 0; g2 < G; ++g2) {
+          if (row_ok && col_active[g2]) {
+            VecLoad<VEC>::ld(irow + gx[g2], buf[j][g2]);
+            if (M2D) mk[j][g2] = ldm_packed<VEC>(irow_m2 + gx[g2]);
+          }
         }
         irow += row_step;
         if (M2D) irow_m2 += row_step;
@@ -210,15 +232,18 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
       ik += MB;
     } else {
       const int yy = y_first + dir * ik;
-      const bool act = col_active && (ik < n_rows) && (yy >= 0) && (yy < p.ny);
+      const bool row_ok = (ik < n_rows) && (yy >= 0) && (yy < p.ny);
       const int m0 = ichunk * MB;
-      const float* q = irow + (long long)m0 * mstride;
 #pragma unroll
-      for (int j = 0; j < MB; ++j) {
-        if (act && (FULL || m0 + j < R)) VecLoad<VEC>::ld(q, buf[j]);
-        q += mstride;
+      for (int g2 = 0; g2 < G; ++g2) {
+        const float* q = irow + (long long)m0 * mstride + gx[g2];
+#pragma unroll
+        for (int j = 0; j < MB; ++j) {
+          if (row_ok && col_active[g2] && (FULL || m0 + j < R)) VecLoad<VEC>::ld(q, buf[j][g2]);
+          q += mstride;
+        }
+        if (M2D && row_ok && col_active[g2] && ichunk == 0) mk[0][g2] = ldm_packed<VEC>(irow_m2 + gx[g2]);
       }
-      if (M2D && act && ichunk == 0) mk[0] = ldm_packed<VEC>(irow_m2);
       if (++ichunk == n_chunks) {
         ichunk = 0; ++ik;
         irow += row_step;
@@ -227,25 +252,39 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
     }
   };
 
-  auto accumulate = [&](const float (&d)[VEC], unsigned m2) {
+  auto accumulate = [&](const float (&d)[VEC], unsigned m2, float (&acc)[VEC], bool flagged, int m,
+                        unsigned long long& ne) {
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       nanacc = max_nan(nanacc, fabsf(d[v]));
-      float tv = truth_value_t<TM>(d[v], thr);
-      if (M2D) tv = (((m2 >> (8 * v)) & 0xffu) != 0) ? tv : 0.f;
-      P[v] += tv;
+      float tv = truth_value_sum<TM>(d[v], thr);
+      bool valid = true;
+      if (M2D) { valid = ((m2 >> (8 * v)) & 0xffu) != 0; tv = valid ? tv : 0.f; }
+      acc[v] += tv;
+      if (flagged) { if (!valid || truth_not_one(d[v], thr)) ne |= 1ull << m; }
     }
   };
 
-  auto consume = [&](float (&buf)[MB][VEC], unsigned (&mk)[ROWS ? MB : 1]) {
+  auto consume = [&](float (&buf)[MB][G][VEC], unsigned (&mk)[MKN][G]) {
     if (ROWS) {
 #pragma unroll
       for (int j = 0; j < MB; ++j) {
         const int k = ck + j;
         if (k < n_rows) {
           const int yy = y_first + dir * k;
-          if (col_active && (yy >= 0) && (yy < p.ny)) accumulate(buf[j], M2D ? mk[j] : 0u);
-          flag_pass(yy);
+          if ((yy >= 0) && (yy < p.ny)) {
+            const bool flagged = !sum_only && (strip_band || yy <= r || yy >= p.ny - 1 - r);
+            if (flagged) {
+#pragma unroll
+              for (int g2 = 0; g2 < G; ++g2)
+                if (col_active[g2]) accumulate(buf[j][g2], M2D ? mk[j][g2] : 0u, P[g2], true, 0, ne_row[g2]);
+              row_flags_done(yy);
+            } else {
+#pragma unroll
+              for (int g2 = 0; g2 < G; ++g2)
+                if (col_active[g2]) accumulate(buf[j][g2], M2D ? mk[j][g2] : 0u, P[g2], false, 0, ne_row[g2]);
+            }
+          }
           finish_row(k);
         }
       }
@@ -253,16 +292,28 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
     } else {
       if (ck < n_rows) {
         const int yy = y_first + dir * ck;
-        if (col_active && (yy >= 0) && (yy < p.ny)) {
-          if (M2D && cchunk == 0) cur_m2 = mk[0];
+        const bool in_dom = (yy >= 0) && (yy < p.ny);
+        if (in_dom) {
           const int m0 = cchunk * MB;
+          const bool flagged = !sum_only && (strip_band || yy <= r || yy >= p.ny - 1 - r);
 #pragma unroll
-          for (int j = 0; j < MB; ++j)
-            if (FULL || m0 + j < R) accumulate(buf[j], cur_m2);
+          for (int g2 = 0; g2 < G; ++g2) {
+            if (!col_active[g2]) continue;
+            if (M2D && cchunk == 0) cur_m2[g2] = mk[0][g2];
+            if (flagged) {
+#pragma unroll
+              for (int j = 0; j < MB; ++j)
+                if (FULL || m0 + j < R) accumulate(buf[j][g2], cur_m2[g2], P[g2], true, m0 + j, ne_row[g2]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < MB; ++j)
+                if (FULL || m0 + j < R) accumulate(buf[j][g2], cur_m2[g2], P[g2], false, 0, ne_row[g2]);
+            }
+          }
         }
         if (++cchunk == n_chunks) {
           cchunk = 0;
-          flag_pass(yy);
+          if (in_dom) row_flags_done(yy);
           finish_row(ck);
           ++ck;
         }
@@ -270,10 +321,12 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
     }
   };
 
-  float bufA[MB][VEC], bufB[MB][VEC];
-  unsigned mkA[ROWS ? MB : 1], mkB[ROWS ? MB : 1];
+  float bufA[MB][G][VEC], bufB[MB][G][VEC];
+  unsigned mkA[MKN][G], mkB[MKN][G];
 #pragma unroll
-  for (int j = 0; j < (ROWS ? MB : 1); ++j) { mkA[j] = 0x01010101u; mkB[j] = 0x01010101u; }
+  for (int j = 0; j < MKN; ++j)
+#pragma unroll
+    for (int g2 = 0; g2 < G; ++g2) { mkA[j][g2] = 0x01010101u; mkB[j][g2] = 0x01010101u; }
   issue(bufA, mkA);
   while (ck < n_rows) {
     issue(bufB, mkB);
@@ -287,9 +340,7 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
     if (lane == 0) atomicOr(reinterpret_cast<unsigned*>(p.status), 1u);
   }
   if (!sum_only) {
-    const bool left = colband && (gx_raw + VEC - 1 <= r);
-    const bool right = colband && (gx_raw >= p.nx - 1 - r);
-    unsigned long long masks[4] = {ne_top, ne_bot, left ? ne_col : 0ull, right ? ne_col : 0ull};
+    unsigned long long masks[4] = {ne_top, ne_bot, ne_left, ne_right};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const unsigned lo32 = __reduce_or_sync(0xffffffffu, (unsigned)masks[k]);
@@ -307,18 +358,18 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
   }
 }
 
-inline size_t sq_warp_smem_bytes(int vec, int nb) {
-  const int WS = 32 * vec;
+inline size_t sq_warp_smem_bytes(int vec, int groups, int nb) {
+  const int WS = 32 * vec * groups;
   return (size_t)((nb + 2) & ~1) * 8 + (size_t)kSqWarpsPerBlock * ((size_t)(WS + 2) * 8 + (size_t)nb * WS * 4);
 }
 
 template <int VEC>
 int launch_square_warp_vec(const SqParams& p, const SqWarpGeom& g, int tm, bool m2d, cudaStream_t st);
 
-template <int VEC, int TM, bool M2D, bool ROWS, bool FULL, int MB>
+template <int VEC, int G, int TM, bool M2D, bool ROWS, bool FULL, int MB>
 static int launch_square_warp_one(const SqParams& p, const SqWarpGeom& g, cudaStream_t st) {
-  auto kern = square_warp_kernel<VEC, TM, M2D, ROWS, FULL, MB>;
-  const size_t smem = sq_warp_smem_bytes(VEC, p.nb);
+  auto kern = square_warp_kernel<VEC, G, TM, M2D, ROWS, FULL, MB>;
+  const size_t smem = sq_warp_smem_bytes(VEC, G, p.nb);
   NBH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = (g.n_tasks + kSqWarpsPerBlock - 1) / kSqWarpsPerBlock;
   NBH_REQUIRE(blocks < (1LL << 31), "too many blocks (%lld); split the launch", blocks);
@@ -327,13 +378,22 @@ static int launch_square_warp_one(const SqParams& p, const SqWarpGeom& g, cudaSt
   return 0;
 }
 
-template <int VEC, int TM, bool M2D>
+// 36 floats per register buffer: MB * G * VEC == 36 (members mode), 16 (rows mode)
+template <int VEC, int G, int TM, bool M2D>
 static int launch_square_warp_mode(const SqParams& p, const SqWarpGeom& g, cudaStream_t st) {
-  constexpr int MBR = VEC == 4 ? 4 : 8;
-  constexpr int MBM = VEC == 4 ? 9 : 18;
-  if (p.n_members == 1) return launch_square_warp_one<VEC, TM, M2D, true, true, MBR>(p, g, st);
-  if (p.n_members % MBM == 0) return launch_square_warp_one<VEC, TM, M2D, false, true, MBM>(p, g, st);
-  return launch_square_warp_one<VEC, TM, M2D, false, false, MBM>(p, g, st);
+  constexpr int MBR = 16 / (VEC * G) > 0 ? 16 / (VEC * G) : 1;
+  constexpr int MBM = 36 / (VEC * G) > 18 ? 18 : 36 / (VEC * G);
+  if (p.n_members == 1) return launch_square_warp_one<VEC, G, TM, M2D, true, true, MBR>(p, g, st);
+  if (p.n_members % MBM == 0) return launch_square_warp_one<VEC, G, TM, M2D, false, true, MBM>(p, g, st);
+  return launch_square_warp_one<VEC, G, TM, M2D, false, false, MBM>(p, g, st);
+}
+
+template <int VEC, int TM, bool M2D>
+static int launch_square_warp_groups(const SqParams& p, const SqWarpGeom& g, cudaStream_t st) {
+  if (g.WS == 32 * VEC) return launch_square_warp_mode<VEC, 1, TM, M2D>(p, g, st);
+  if constexpr (VEC < 4) return launch_square_warp_mode<VEC, 2, TM, M2D>(p, g, st);
+  nbh::set_error("unsupported strip width %d", g.WS);
+  return 1;
 }
 
 #define NBH_DEFINE_SQUARE_WARP_VEC(VEC)                                                              \
@@ -341,12 +401,12 @@ static int launch_square_warp_mode(const SqParams& p, const SqWarpGeom& g, cudaS
   int launch_square_warp_vec<VEC>(const SqParams& p, const SqWarpGeom& g, int tm, bool m2d,          \
                                   cudaStream_t st) {                                                 \
     switch ((tm << 1) | (m2d ? 1 : 0)) {                                                             \
-      case 0: return launch_square_warp_mode<VEC, 0, false>(p, g, st);                               \
-      case 1: return launch_square_warp_mode<VEC, 0, true>(p, g, st);                                \
-      case 2: return launch_square_warp_mode<VEC, 1, false>(p, g, st);                               \
-      case 3: return launch_square_warp_mode<VEC, 1, true>(p, g, st);                                \
-      case 4: return launch_square_warp_mode<VEC, 2, false>(p, g, st);                               \
-      default: return launch_square_warp_mode<VEC, 2, true>(p, g, st);                               \
+      case 0: return launch_square_warp_groups<VEC, 0, false>(p, g, st);                               \
+      case 1: return launch_square_warp_groups<VEC, 0, true>(p, g, st);                                \
+      case 2: return launch_square_warp_groups<VEC, 1, false>(p, g, st);                               \
+      case 3: return launch_square_warp_groups<VEC, 1, true>(p, g, st);                                \
+      case 4: return launch_square_warp_groups<VEC, 2, false>(p, g, st);                               \
+      default: return launch_square_warp_groups<VEC, 2, true>(p, g, st);                               \
     }                                                                                                \
   }
 
