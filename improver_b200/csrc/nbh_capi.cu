@@ -131,14 +131,9 @@ int make_thr_dev(const NbhThreshold& h, ThrDev* d, bool ma_arith) {
   d->den2_hi = 2.0f * d->den_hi;
   d->rcph_lo = (float)(0.5 / (double)d->den_lo);
   d->rcph_hi = (float)(0.5 / (double)d->den_hi);
-  // convex (slope below thr smaller than above) -> max of the two lines; concave -> min
-  const float sigma = (d->rcph_lo <= d->rcph_hi) ? 1.0f : -1.0f;
-  d->fs_lo = sigma * d->rcph_lo;
-  d->fs_hi = sigma * d->rcph_hi;
-  d->fc_hi = sigma * 0.5f;
   const bool invert = h.op >= NBH_OP_LT;
-  d->f_mul = invert ? -sigma : sigma;
-  d->f_add = invert ? 1.0f : 0.0f;
+  d->fs_lo = invert ? -d->rcph_lo : d->rcph_lo;
+  d->fs_hi = invert ? -d->rcph_hi : d->rcph_hi;
   find_one_interval(d);
   return 0;
 }

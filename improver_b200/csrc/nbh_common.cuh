@@ -46,9 +46,7 @@ struct ThrDev {
   int op;         // NBH_OP_*
   double lo64;    // bounds[0] unrounded (np.ma arithmetic promotes to float64)
   // branch-free evaluation used inside the neighbourhood sums (truth_value_fast)
-  float fs_lo, fs_hi;   // sigma * 0.5/den_lo, sigma * 0.5/den_hi
-  float fc_hi;          // sigma * 0.5
-  float f_mul, f_add;   // result = sat(m * f_mul + f_add): (sigma, 0) or (-sigma, 1) for "less than"
+  float fs_lo, fs_hi;   // +-0.5/den_lo, +-0.5/den_hi (negated for "less than" comparisons)
   // exact "truth value == 1" test on the data itself (edge-band flags of the
   // trimming fix-up): one_lo <= d <= one_hi  <=>  truth_value(d) == 1.0f
   float one_lo, one_hi;
@@ -114,18 +112,18 @@ __device__ __forceinline__ float truth_value_t(float d, const ThrDev& p) {
   return v;
 }
 
-// Branch-free fuzzy truth value for use inside neighbourhood sums.  The
-// membership function is piecewise linear through (lo,0), (thr,.5), (hi,1):
-// the min (concave, sigma=-1 via max of negated lines) or max (convex,
-// sigma=+1) of its two lines, saturated to [0,1].  Each line is evaluated as
-// (d - base) * slope, so there is no cancellation: the result is within 2 ulp
-// (1.2e-7) of the correctly rounded reference value and exactly 0 / 1 on the
-// plateaus.  6 instructions instead of 13; the exact form (truth_value_t<2>)
-// stays in use wherever truth values themselves are output or compared.
+// Fast fuzzy truth value for use inside neighbourhood sums.  The membership
+// function is piecewise linear through (lo,0), (thr,.5), (hi,1); both pieces
+// pass through (thr, .5), so with a = d - thr it is sat(.5 + a * slope) with
+// the slope picked by the sign of a.  "less than" comparisons negate the
+// slopes (1 - v = .5 - a * slope).  Four instructions; within 1e-7 of the
+// correctly rounded reference value, exactly 0 / 1 beyond the bounds.  The
+// exact form (truth_value_t<2>) stays in use wherever truth values themselves
+// are output or compared.
 __device__ __forceinline__ float truth_value_fast(float d, const ThrDev& p) {
-  const float g_lo = __fmul_rn(__fsub_rn(d, p.lo), p.fs_lo);
-  const float g_hi = __fmaf_rn(__fsub_rn(d, p.thr), p.fs_hi, p.fc_hi);
-  return __saturatef(__fmaf_rn(fmaxf(g_lo, g_hi), p.f_mul, p.f_add));
+  const float a = __fsub_rn(d, p.thr);
+  const float s = (a < 0.0f) ? p.fs_lo : p.fs_hi;
+  return __saturatef(__fmaf_rn(a, s, 0.5f));
 }
 
 // truth_value(d) != 1 without evaluating it (bounds found on the host by

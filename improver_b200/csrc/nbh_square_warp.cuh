@@ -18,7 +18,12 @@
 
 namespace nbh {
 
-constexpr int kSqWarpsPerBlock = 4;
+constexpr int kSqWarpsPerBlock = 1;   // one warp per block: everything derived from blockIdx is
+                                      // provably uniform, so row/member pointers live in uniform registers
+
+__device__ __forceinline__ const float* byte_offset(const float* base, unsigned bytes) {
+  return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + bytes);
+}
 
 struct SqWarpGeom {
   int WS;        // columns loaded per warp (32 * VEC * groups)
@@ -29,7 +34,7 @@ struct SqWarpGeom {
 };
 
 template <int VEC, int G, int TM, bool M2D, bool ROWS, bool FULL, int MB>
-__global__ void __launch_bounds__(kSqWarpsPerBlock * 32, 3)
+__global__ void __launch_bounds__(kSqWarpsPerBlock * 32, 12)
 square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -113,21 +118,24 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
   const int R = p.n_members;
   const int n_chunks = ROWS ? 1 : (R + MB - 1) / MB;
   const long long mstride = p.member_stride;
-  const long long row_step = (long long)dir * p.nx;
   const float* in_plane = p.in + plane * p.plane_stride;
+  unsigned goff[G];
+#pragma unroll
+  for (int g2 = 0; g2 < G; ++g2) goff[g2] = (unsigned)gx[g2] * 4u;
   const long long obase0 = (plane * p.n_thr + t) * (long long)p.ny * p.nx;
 
   // issue / consume cursors: row counters k (0 .. n_rows) and member chunk index
   int ik = 0, ichunk = 0, ck = 0, cchunk = 0;
-  const float* irow = in_plane + (long long)y_first * p.nx;           // row base (column 0)
-  const uint8_t* irow_m2 = M2D ? p.mask2d + (long long)y_first * p.nx : nullptr;
 
   // ---- one finished input row: ring, vertical sums, horizontal pass, store ----
-  auto finish_row = [&](int k) {
+  auto finish_row = [&](int k, bool row_in_dom) {
 #pragma unroll
     for (int g2 = 0; g2 < G; ++g2)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
+        // loads are unconditional (clamped addresses): rows outside the domain and
+        // lanes outside the strip's columns contribute zero (zero padding)
+        if (!row_in_dom || !col_active[g2]) P[g2][v] = 0.f;
         const int ri = slot * WS + c0[g2] + v;
         const float old = ring[ri];
         ring[ri] = P[g2][v];
@@ -213,47 +221,48 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
   };
 
   constexpr int MKN = ROWS ? MB : 1;
+  const uint8_t* m2_base = M2D ? p.mask2d : nullptr;
+  auto row_ptr = [&](int k) {                 // clamped: always a valid row of this plane
+    const int yy = min(max(y_first + dir * min(k, n_rows - 1), 0), p.ny - 1);
+    return (long long)yy * p.nx;
+  };
   auto issue = [&](float (&buf)[MB][G][VEC], unsigned (&mk)[MKN][G]) {
     if (ROWS) {
 #pragma unroll
       for (int j = 0; j < MB; ++j) {
-        const int yy = y_first + dir * (ik + j);
-        const bool row_ok = (ik + j < n_rows) && (yy >= 0) && (yy < p.ny);
+        const long long off = row_ptr(ik + j);
 #pragma unroll
         for (int g2 = 0; g2 < G; ++g2) {
-          if (row_ok && col_active[g2]) {
-            VecLoad<VEC>::ld(irow + gx[g2], buf[j][g2]);
-            if (M2D) mk[j][g2] = ldm_packed<VEC>(irow_m2 + gx[g2]);
-          }
+          VecLoad<VEC>::ld(byte_offset(in_plane + off, goff[g2]), buf[j][g2]);
+          if (M2D) mk[j][g2] = ldm_packed<VEC>(m2_base + off + gx[g2]);
         }
-        irow += row_step;
-        if (M2D) irow_m2 += row_step;
       }
       ik += MB;
     } else {
-      const int yy = y_first + dir * ik;
-      const bool row_ok = (ik < n_rows) && (yy >= 0) && (yy < p.ny);
+      const long long off = row_ptr(ik);
       const int m0 = ichunk * MB;
+      // warp-uniform member pointer + 32-bit per-lane byte offset
+      const float* q = in_plane + off + (long long)m0 * mstride;
 #pragma unroll
-      for (int g2 = 0; g2 < G; ++g2) {
-        const float* q = irow + (long long)m0 * mstride + gx[g2];
+      for (int j = 0; j < MB; ++j) {
+        if (FULL || m0 + j < R) {
 #pragma unroll
-        for (int j = 0; j < MB; ++j) {
-          if (row_ok && col_active[g2] && (FULL || m0 + j < R)) VecLoad<VEC>::ld(q, buf[j][g2]);
-          q += mstride;
+          for (int g2 = 0; g2 < G; ++g2) VecLoad<VEC>::ld(byte_offset(q, goff[g2]), buf[j][g2]);
         }
-        if (M2D && row_ok && col_active[g2] && ichunk == 0) mk[0][g2] = ldm_packed<VEC>(irow_m2 + gx[g2]);
+        q += mstride;
       }
-      if (++ichunk == n_chunks) {
-        ichunk = 0; ++ik;
-        irow += row_step;
-        if (M2D) irow_m2 += row_step;
+      if (M2D && ichunk == 0) {
+#pragma unroll
+        for (int g2 = 0; g2 < G; ++g2) mk[0][g2] = ldm_packed<VEC>(m2_base + off + gx[g2]);
       }
+      if (++ichunk == n_chunks) { ichunk = 0; ++ik; }
     }
   };
 
-  auto accumulate = [&](const float (&d)[VEC], unsigned m2, float (&acc)[VEC], bool flagged, int m,
-                        unsigned long long& ne) {
+  // one loaded VEC group of one member: threshold, mask, accumulate; the flagged
+  // copy also records "saw a value != 1" in bit `bit` of nel
+  auto accumulate = [&](const float (&d)[VEC], unsigned m2, float (&acc)[VEC], bool flagged, unsigned bit,
+                        unsigned& nel) {
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       nanacc = max_nan(nanacc, fabsf(d[v]));
@@ -261,7 +270,7 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
       bool valid = true;
       if (M2D) { valid = ((m2 >> (8 * v)) & 0xffu) != 0; tv = valid ? tv : 0.f; }
       acc[v] += tv;
-      if (flagged) { if (!valid || truth_not_one(d[v], thr)) ne |= 1ull << m; }
+      if (flagged) { if (!valid || truth_not_one(d[v], thr)) nel |= bit; }
     }
   };
 
@@ -272,20 +281,22 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
         const int k = ck + j;
         if (k < n_rows) {
           const int yy = y_first + dir * k;
-          if ((yy >= 0) && (yy < p.ny)) {
-            const bool flagged = !sum_only && (strip_band || yy <= r || yy >= p.ny - 1 - r);
-            if (flagged) {
+          const bool in_dom = (yy >= 0) && (yy < p.ny);
+          const bool flagged = in_dom && !sum_only && (strip_band || yy <= r || yy >= p.ny - 1 - r);
+          if (flagged) {
 #pragma unroll
-              for (int g2 = 0; g2 < G; ++g2)
-                if (col_active[g2]) accumulate(buf[j][g2], M2D ? mk[j][g2] : 0u, P[g2], true, 0, ne_row[g2]);
-              row_flags_done(yy);
-            } else {
-#pragma unroll
-              for (int g2 = 0; g2 < G; ++g2)
-                if (col_active[g2]) accumulate(buf[j][g2], M2D ? mk[j][g2] : 0u, P[g2], false, 0, ne_row[g2]);
+            for (int g2 = 0; g2 < G; ++g2) {
+              unsigned nel = 0;
+              accumulate(buf[j][g2], M2D ? mk[j][g2] : 0u, P[g2], true, 1u, nel);
+              ne_row[g2] |= nel;
             }
+            row_flags_done(yy);
+          } else {
+            unsigned nel = 0;
+#pragma unroll
+            for (int g2 = 0; g2 < G; ++g2) accumulate(buf[j][g2], M2D ? mk[j][g2] : 0u, P[g2], false, 0u, nel);
           }
-          finish_row(k);
+          finish_row(k, in_dom);
         }
       }
       ck += MB;
@@ -293,28 +304,27 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
       if (ck < n_rows) {
         const int yy = y_first + dir * ck;
         const bool in_dom = (yy >= 0) && (yy < p.ny);
-        if (in_dom) {
-          const int m0 = cchunk * MB;
-          const bool flagged = !sum_only && (strip_band || yy <= r || yy >= p.ny - 1 - r);
+        const int m0 = cchunk * MB;
+        const bool flagged = in_dom && !sum_only && (strip_band || yy <= r || yy >= p.ny - 1 - r);
 #pragma unroll
-          for (int g2 = 0; g2 < G; ++g2) {
-            if (!col_active[g2]) continue;
-            if (M2D && cchunk == 0) cur_m2[g2] = mk[0][g2];
-            if (flagged) {
+        for (int g2 = 0; g2 < G; ++g2) {
+          if (M2D && cchunk == 0) cur_m2[g2] = mk[0][g2];
+          unsigned nel = 0;
+          if (flagged) {
 #pragma unroll
-              for (int j = 0; j < MB; ++j)
-                if (FULL || m0 + j < R) accumulate(buf[j][g2], cur_m2[g2], P[g2], true, m0 + j, ne_row[g2]);
-            } else {
+            for (int j = 0; j < MB; ++j)
+              if (FULL || m0 + j < R) accumulate(buf[j][g2], cur_m2[g2], P[g2], true, 1u << j, nel);
+            ne_row[g2] |= (unsigned long long)nel << m0;
+          } else {
 #pragma unroll
-              for (int j = 0; j < MB; ++j)
-                if (FULL || m0 + j < R) accumulate(buf[j][g2], cur_m2[g2], P[g2], false, 0, ne_row[g2]);
-            }
+            for (int j = 0; j < MB; ++j)
+              if (FULL || m0 + j < R) accumulate(buf[j][g2], cur_m2[g2], P[g2], false, 0u, nel);
           }
         }
         if (++cchunk == n_chunks) {
           cchunk = 0;
-          if (in_dom) row_flags_done(yy);
-          finish_row(ck);
+          if (flagged) row_flags_done(yy);
+          finish_row(ck, in_dom);
           ++ck;
         }
       }
