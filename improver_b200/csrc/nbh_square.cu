@@ -49,14 +49,15 @@ __device__ __forceinline__ float load_value(const SqParams& p, long long plane, 
 
 template <int TM>
 __global__ void __launch_bounds__(256)
-square_stats_kernel(const SqParams p, int chunks) {
-  long long bid = blockIdx.x;
-  const int chunk = (int)(bid % chunks); bid /= chunks;
+square_stats_kernel(const SqParams p, int chunks, const int* suspects, const int* n_suspects) {
+ const long long n_work = (long long)(*n_suspects) * chunks;
+ for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
+  const int chunk = (int)(work % chunks);
+  const long long sidx = suspects[work / chunks];
+  long long bid = sidx;
   const int t = (int)(bid % p.n_thr); bid /= p.n_thr;
   const int m = (int)(bid % p.n_members);
   const long long plane = bid / p.n_members;
-  const long long sidx = (plane * p.n_members + m) * p.n_thr + t;
-  if (p.edge_flags[sidx] == 0xFu) return;
   const ThrDev thr = p.thr.t[TM ? t : 0];
   const long long npts = (long long)p.ny * p.nx;
   int b[8] = {INT_MAX, -1, INT_MAX, -1, INT_MAX, -1, INT_MAX, -1};
@@ -85,6 +86,7 @@ square_stats_kernel(const SqParams p, int chunks) {
     atomicMin(&s->x1min, b[6]); atomicMax(&s->x1max, b[7]);
     atomicMin(&s->vmin_key, kmin); atomicMax(&s->vmax_key, kmax);
   }
+ }
 }
 
 __device__ __forceinline__ long long grown_area(int ymin, int ymax, int xmin, int xmax, int h, int ny,
@@ -97,14 +99,15 @@ __device__ __forceinline__ long long grown_area(int ymin, int ymax, int xmin, in
 
 template <int TM>
 __global__ void __launch_bounds__(256)
-square_fixup_kernel(const SqParams p, int chunks) {
-  long long bid = blockIdx.x;
-  const int chunk = (int)(bid % chunks); bid /= chunks;
+square_fixup_kernel(const SqParams p, int chunks, const int* suspects, const int* n_suspects) {
+ const long long n_work = (long long)(*n_suspects) * chunks;
+ for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
+  const int chunk = (int)(work % chunks);
+  const long long sidx = suspects[work / chunks];
+  long long bid = sidx;
   const int t = (int)(bid % p.n_thr); bid /= p.n_thr;
   const int m = (int)(bid % p.n_members);
   const long long plane = bid / p.n_members;
-  const long long sidx = (plane * p.n_members + m) * p.n_thr + t;
-  if (p.edge_flags[sidx] == 0xFu) return;
   const SliceStats s = p.stats[sidx];
   const int h = p.r;
   long long size = (long long)p.ny * p.nx;
@@ -113,7 +116,7 @@ square_fixup_kernel(const SqParams p, int chunks) {
   if (a0 < size) { size = a0; e = 0; }
   long long a1 = grown_area(s.y1min, s.y1max, s.x1min, s.x1max, h, p.ny, p.nx, &y1a, &y1b, &x1a, &x1b);
   if (a1 < size) { size = a1; e = 1; }
-  if (e != 1 || size == 0) return;
+  if (e != 1 || size == 0) continue;
   if (chunk == 0 && threadIdx.x == 0) atomicAdd(p.status + 1, 1);
   const ThrDev thr = p.thr.t[TM ? t : 0];
   const float vmin = key_float(s.vmin_key), vmax = key_float(s.vmax_key);
@@ -150,10 +153,20 @@ square_fixup_kernel(const SqParams p, int chunks) {
       atomicAdd(p.out + o, (float)(((double)(float)fixed - (double)old) * p.inv_members));
     }
   }
+ }
 }
 
-__global__ void init_stats_kernel(unsigned* flags, SliceStats* stats, long long n, unsigned init_bits) {
+// Slices whose four edge bands are not all known to contain a value != 1.
+__global__ void collect_suspects_kernel(const unsigned* flags, long long n, int* suspects, int* n_suspects) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (flags[i] != 0xFu) suspects[atomicAdd(n_suspects, 1)] = (int)i;
+}
+
+__global__ void init_stats_kernel(unsigned* flags, SliceStats* stats, long long n, unsigned init_bits,
+                                  int* n_suspects) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *n_suspects = 0;
   if (i >= n) return;
   flags[i] = init_bits;
   SliceStats s;
@@ -279,10 +292,12 @@ static bool plan_square_warp(const NbhDesc& d, int vec, SqWarpGeom* g) {
   const int r = d.cells;
   const bool wrap = (d.flags & NBH_WRAP_X) != 0;
   // one or two VEC groups per lane: pick the strip width with the fewest idle lanes
+  // (two groups per lane waste fewer lanes but need > 128 registers, which costs
+  // more in occupancy than it gains on B200: opt-in only)
   double best = 0.0;
-  int forced = env_int("NBH_SQW_GROUPS", 0);
+  const int forced = env_int("NBH_SQW_GROUPS", 1);
   for (int groups = 1; groups <= (vec < 4 ? 2 : 1); ++groups) {
-    if (forced && groups != forced) continue;
+    if (groups != forced && !(forced > 2)) continue;
     const int WS = 32 * vec * groups;
     const int hl = (r + vec - 1) / vec * vec;
     const int W = (WS - hl - r) / vec * vec;
@@ -300,22 +315,13 @@ static bool plan_square_warp(const NbhDesc& d, int vec, SqWarpGeom* g) {
   const long long units = d.n_planes * (long long)max(d.n_thresholds, 1) * g->n_strips;
   int ysegs = env_int("NBH_SQW_YSEGS", 0);
   if (ysegs <= 0) {
-    // Every y segment re-reads 2r halo rows (mostly from L2) and the last,
-    // partially filled wave of warp tasks idles part of the machine: pick the
-    // segmentation minimising halo x tail.
-    const double slots = (double)sm_count() * 12;
-    double best_cost = 1e30;
-    ysegs = 1;
-    for (int cand = 1; cand <= 64; ++cand) {
-      const int seg_rows = (d.ny + cand - 1) / cand;
-      if (cand > 1 && seg_rows < max(32, 6 * r)) break;
-      if ((d.ny + seg_rows - 1) / seg_rows != cand) continue;
-      const double waves = (double)units * cand / slots;
-      const double tail = ceil(waves) / waves;
-      const double halo = 1.0 + 2.0 * r / seg_rows;
-      const double cost = tail * halo;
-      if (cost < best_cost) { best_cost = cost; ysegs = cand; }
-    }
+    // Warps are scheduled dynamically as blocks retire, so many small tasks
+    // balance better than few large ones; every y segment re-reads 2r halo rows
+    // (mostly L2 hits thanks to the alternating march direction).  Measured on
+    // B200 (profiles/): ~5 tasks per resident warp slot is the sweet spot.
+    const double slots = (double)sm_count() * env_int("NBH_SQW_WPS", 16);
+    const int max_segs = max(1, d.ny / max(32, 6 * r));
+    ysegs = (int)min((double)max_segs, max(1.0, ceil(5.0 * slots / (double)units)));
   }
   ysegs = max(1, min(ysegs, d.ny));
   g->seg_rows = (d.ny + ysegs - 1) / ysegs;
@@ -327,6 +333,8 @@ static bool plan_square_warp(const NbhDesc& d, int vec, SqWarpGeom* g) {
 struct SqWorkspace {
   unsigned* edge_flags;
   SliceStats* stats;
+  int* suspects;
+  int* n_suspects;
   double* rcp_count;
   uint16_t* tmp;
   size_t total;
@@ -338,6 +346,8 @@ static void carve_workspace(const NbhDesc& d, void* ws, SqWorkspace* w) {
   unsigned char* base = reinterpret_cast<unsigned char*>(ws);
   w->edge_flags = reinterpret_cast<unsigned*>(base + off); off = align_up(off + nslices * 4, 256);
   w->stats = reinterpret_cast<SliceStats*>(base + off); off = align_up(off + nslices * sizeof(SliceStats), 256);
+  w->suspects = reinterpret_cast<int*>(base + off); off = align_up(off + nslices * 4, 256);
+  w->n_suspects = reinterpret_cast<int*>(base + off); off = align_up(off + 4, 256);
   w->rcp_count = reinterpret_cast<double*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 8, 256);
   w->tmp = reinterpret_cast<uint16_t*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 2, 256);
   w->total = off;
@@ -410,8 +420,9 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   const bool sum_only = (d->flags & NBH_SUM_ONLY) != 0;
   NBH_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int32_t), st));
   const unsigned init_bits = sum_only ? 0xFu : ((d->flags & NBH_WRAP_X) ? 0xCu : 0u);
+  NBH_REQUIRE(nslices < (1LL << 31), "too many slices in one launch (%lld)", nslices);
   init_stats_kernel<<<(unsigned)((nslices + 255) / 256), 256, 0, st>>>(w.edge_flags, w.stats, nslices,
-                                                                    init_bits);
+                                                                    init_bits, w.n_suspects);
   if (d->mask2d && !masknd && !sum_only) {
     const long long n = (long long)d->ny * d->nx;
     count_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d->mask2d, w.tmp, d->ny, d->nx,
@@ -443,21 +454,23 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   }
   if (rc) return rc;
   if (!sum_only) {
+    // trimming fix-up: nothing to do (three tiny launches) unless a slice is suspicious
     const int chunks = 32;
-    const long long fb = nslices * chunks;
-    NBH_REQUIRE(fb < (1LL << 31), "too many fix-up blocks");
+    collect_suspects_kernel<<<(unsigned)((nslices + 255) / 256), 256, 0, st>>>(w.edge_flags, nslices,
+                                                                            w.suspects, w.n_suspects);
+    const unsigned fb = (unsigned)min((long long)sm_count() * 8, nslices * chunks);
     switch (tm) {
       case 0:
-        square_stats_kernel<0><<<(unsigned)fb, 256, 0, st>>>(p, chunks);
-        square_fixup_kernel<0><<<(unsigned)fb, 256, 0, st>>>(p, chunks);
+        square_stats_kernel<0><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects);
+        square_fixup_kernel<0><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects);
         break;
       case 1:
-        square_stats_kernel<1><<<(unsigned)fb, 256, 0, st>>>(p, chunks);
-        square_fixup_kernel<1><<<(unsigned)fb, 256, 0, st>>>(p, chunks);
+        square_stats_kernel<1><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects);
+        square_fixup_kernel<1><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects);
         break;
       default:
-        square_stats_kernel<2><<<(unsigned)fb, 256, 0, st>>>(p, chunks);
-        square_fixup_kernel<2><<<(unsigned)fb, 256, 0, st>>>(p, chunks);
+        square_stats_kernel<2><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects);
+        square_fixup_kernel<2><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects);
         break;
     }
     NBH_CHECK_CUDA(cudaGetLastError());

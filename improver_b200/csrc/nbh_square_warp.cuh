@@ -34,7 +34,7 @@ struct SqWarpGeom {
 };
 
 template <int VEC, int G, int TM, bool M2D, bool ROWS, bool FULL, int MB>
-__global__ void __launch_bounds__(kSqWarpsPerBlock * 32, 12)
+__global__ void __launch_bounds__(kSqWarpsPerBlock * 32, 16)
 square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

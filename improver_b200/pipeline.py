@@ -17,7 +17,7 @@ import torch
 
 from . import _lib, engine
 
-LAUNCHES_PER_FUSED_CALL = 4     # init_stats, square_kernel, square_stats, square_fixup
+LAUNCHES_PER_FUSED_CALL = 5     # init_stats, square kernel, collect_suspects, square_stats, square_fixup
 
 
 def pinned_like(t: torch.Tensor) -> torch.Tensor:
