@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.path.join(_HERE, "lib", "libimprover_b200.so")
 
 OPS = {">": 0, "gt": 0, "GT": 0, ">=": 1, "ge": 1, "GE": 1,
-       "<": 2, "lt": 2, "LT": 2, "<=": 3, "le": 3, "LE": 3}
+       "<": 2, "lt": 2, "LT": 2, "<=": 3, "le": 3, "LE": 3, "==": 4, "eq": 4, "EQ": 4}
 
 SUM_ONLY, WRAP_X, WEIGHTED = 1, 2, 4
 

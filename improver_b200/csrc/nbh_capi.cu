@@ -39,7 +39,8 @@ static float host_truth(const ThrDev& p, float d) {
       case NBH_OP_GT: b = d > p.thr; break;
       case NBH_OP_GE: b = d >= p.thr; break;
       case NBH_OP_LT: b = d < p.thr; break;
-      default: b = d <= p.thr; break;
+      case NBH_OP_LE: b = d <= p.thr; break;
+      default: b = d == p.thr; break;
     }
     return b ? 1.f : 0.f;
   }
@@ -50,7 +51,7 @@ static float host_truth(const ThrDev& p, float d) {
     const double off = below ? 0.0 : 0.5;
     double v = a * 0.5 / den + off;
     v = std::fmin(std::fmax(v, off), off + 0.5);
-    if (p.op >= NBH_OP_LT) v = 1.0 - v;
+    if ((p.op == NBH_OP_LT || p.op == NBH_OP_LE)) v = 1.0 - v;
     return (float)v;
   }
   const float dc = std::fmin(std::fmax(d, p.lo), p.hi);
@@ -63,7 +64,7 @@ static float host_truth(const ThrDev& p, float d) {
   const float q0 = a * rcph;
   const float rem = std::fmaf(-den2, q0, a);
   float v = std::fmaf(rem, rcph, q0) + off;
-  if (p.op >= NBH_OP_LT) v = 1.0f - v;
+  if ((p.op == NBH_OP_LT || p.op == NBH_OP_LE)) v = 1.0f - v;
   return v;
 }
 
@@ -81,7 +82,8 @@ static float ord2f(uint32_t k) {
 // (the membership function is monotone, so the set is an interval ending at +-inf).
 static void find_one_interval(ThrDev* d) {
   const float inf = INFINITY;
-  const bool decreasing = (d->mode != 1) ? (d->op >= NBH_OP_LT) : (d->op >= NBH_OP_LT);
+  if (d->mode == 1 && d->op == NBH_OP_EQ) { d->one_lo = d->one_hi = d->thr; return; }
+  const bool decreasing = (d->mode != 1) ? ((d->op == NBH_OP_LT || d->op == NBH_OP_LE)) : ((d->op == NBH_OP_LT || d->op == NBH_OP_LE));
   // search over the total order of floats between -inf and +inf
   uint32_t lo = f2ord(-inf), hi = f2ord(inf);
   if (!decreasing) {
@@ -108,7 +110,7 @@ static void find_one_interval(ThrDev* d) {
 // numpy's weak-scalar promotion of the python-float fuzzy bounds.
 int make_thr_dev(const NbhThreshold& h, ThrDev* d, bool ma_arith) {
   memset(d, 0, sizeof(*d));
-  NBH_REQUIRE(h.op >= NBH_OP_GT && h.op <= NBH_OP_LE, "unknown comparison operator code %d", h.op);
+  NBH_REQUIRE(h.op >= NBH_OP_GT && h.op <= NBH_OP_EQ, "unknown comparison operator code %d", h.op);
   d->op = h.op;
   d->thr = (float)h.value;
   if (h.lo == h.hi) {           // threshold.py:438-439
@@ -131,7 +133,7 @@ int make_thr_dev(const NbhThreshold& h, ThrDev* d, bool ma_arith) {
   d->den2_hi = 2.0f * d->den_hi;
   d->rcph_lo = (float)(0.5 / (double)d->den_lo);
   d->rcph_hi = (float)(0.5 / (double)d->den_hi);
-  const bool invert = h.op >= NBH_OP_LT;
+  const bool invert = (h.op == NBH_OP_LT || h.op == NBH_OP_LE);
   d->fs_lo = invert ? -d->rcph_lo : d->rcph_lo;
   d->fs_hi = invert ? -d->rcph_hi : d->rcph_hi;
   find_one_interval(d);

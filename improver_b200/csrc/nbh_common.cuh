@@ -74,7 +74,8 @@ __device__ __forceinline__ float truth_value_t(float d, const ThrDev& p) {
       case NBH_OP_GT: b = d > p.thr; break;
       case NBH_OP_GE: b = d >= p.thr; break;
       case NBH_OP_LT: b = d < p.thr; break;
-      default: b = d <= p.thr; break;
+      case NBH_OP_LE: b = d <= p.thr; break;
+      default: b = d == p.thr; break;
     }
     return b ? 1.0f : 0.0f;
   }
@@ -89,7 +90,7 @@ __device__ __forceinline__ float truth_value_t(float d, const ThrDev& p) {
     const double off = below ? 0.0 : 0.5;
     double v = a * 0.5 / den + off;
     v = fmin(fmax(v, off), off + 0.5);
-    if (p.op >= NBH_OP_LT) v = 1.0 - v;
+    if ((p.op == NBH_OP_LT || p.op == NBH_OP_LE)) v = 1.0 - v;
     return (float)v;
   }
   // fuzzy: where(d < thr, clip((d-lo)*0.5/(thr-lo) + 0, 0, .5),
@@ -108,7 +109,7 @@ __device__ __forceinline__ float truth_value_t(float d, const ThrDev& p) {
   const float q0 = __fmul_rn(a, rcph);
   const float rem = __fmaf_rn(-den2, q0, a);
   float v = __fadd_rn(__fmaf_rn(rem, rcph, q0), off);
-  if (p.op >= NBH_OP_LT) v = __fsub_rn(1.0f, v);     // threshold.py:468-469
+  if ((p.op == NBH_OP_LT || p.op == NBH_OP_LE)) v = __fsub_rn(1.0f, v);     // threshold.py:468-469
   return v;
 }
 

@@ -1,0 +1,93 @@
+"""Neighbourhood array tools with the reference's signatures
+(improver/utilities/neighbourhood_tools.py:13-211).
+
+`rolling_window` / `pad_and_roll` only build strided *views* (no arithmetic)
+and stay on the host.  `boxsum` — the summed-area-table box sum that is the
+reference's square-neighbourhood work-horse — runs on the GPU: the padded
+array is handed to the sliding-window CUDA kernel (engine.neighbourhood with
+sum_only) and the interior is cropped, which is the same quantity as the
+reference's four-corner difference of the cumulative sums.
+"""
+from __future__ import annotations
+
+from typing import Any, Tuple, Union
+
+import numpy as np
+
+
+def rolling_window(input_array: np.ndarray, shape: Tuple[int, int], writeable: bool = False) -> np.ndarray:
+    """neighbourhood_tools.py:13-66."""
+    num_window_dims = len(shape)
+    num_arr_dims = len(input_array.shape)
+    if num_arr_dims < num_window_dims:
+        raise ValueError(
+            "Number of dimensions of the input array must be greater than or "
+            "equal to the length of the neighbourhood shape used for "
+            "constructing rolling window neighbourhoods.")
+    adjshp = (*input_array.shape[:-num_window_dims],
+              *(a - w + 1 for a, w in zip(input_array.shape[-num_window_dims:], shape)),
+              *shape)
+    if any(a <= 0 for a in adjshp):
+        raise RuntimeError(
+            "The calculated shape of the output array view contains a "
+            "dimension that is negative or zero. Each dimension of the "
+            "neighbourhood shape must be less than or equal to the "
+            "corresponding dimension of the input array.")
+    strides = input_array.strides + input_array.strides[-num_window_dims:]
+    return np.lib.stride_tricks.as_strided(input_array, shape=adjshp, strides=strides, writeable=writeable)
+
+
+def pad_and_roll(input_array: np.ndarray, shape: Tuple[int, int], **kwargs: Any) -> np.ndarray:
+    """neighbourhood_tools.py:69-101."""
+    writeable = kwargs.pop("writeable", False)
+    pad_extent = [(0, 0)] * (len(input_array.shape) - len(shape))
+    pad_extent.extend((d // 2, d // 2) for d in shape)
+    input_array = np.pad(input_array, pad_extent, **kwargs)
+    return rolling_window(input_array, shape, writeable=writeable)
+
+
+def pad_boxsum(data: np.ndarray, boxsize: Union[int, Tuple[int, int]], **pad_options: Any) -> np.ndarray:
+    """neighbourhood_tools.py:104-126 (one extra row/column at the top/left)."""
+    boxsize = np.atleast_1d(boxsize)
+    ih, jh = boxsize[0] // 2, boxsize[-1] // 2
+    padding = [(0, 0)] * (data.ndim - 2) + [(ih + 1, ih), (jh + 1, jh)]
+    return np.pad(data, padding, **pad_options)
+
+
+def boxsum(data: np.ndarray, boxsize: Union[int, Tuple[int, int]], cumsum: bool = True,
+           **pad_options: Any) -> np.ndarray:
+    """neighbourhood_tools.py:129-211.  Returns float64 like the reference does
+    for float input (int64 for integer input)."""
+    import torch
+
+    from .. import engine
+
+    boxsize = np.atleast_1d(boxsize)
+    if not issubclass(boxsize.dtype.type, np.integer):
+        raise ValueError("The size of the neighbourhood must be of an integer type.")
+    if not np.all(boxsize % 2):
+        raise ValueError("The size of the neighbourhood must be an odd number.")
+    bi, bj = int(boxsize[0]), int(boxsize[-1])
+    data = np.asarray(data)
+    if pad_options:
+        data = pad_boxsum(data, boxsize, **pad_options)
+    m, n = data.shape[-2] - bi, data.shape[-1] - bj
+    if not cumsum:
+        # input already cumulative: only the four-corner difference remains
+        t = torch.from_numpy(np.ascontiguousarray(data)).cuda()
+        res = (t[..., bi:bi + m, bj:bj + n] - t[..., :m, bj:bj + n]
+               + t[..., :m, :n] - t[..., bi:bi + m, :n])
+        return res.cpu().numpy()
+    if bi != bj:
+        raise NotImplementedError("rectangular boxes are not supported by the CUDA box-sum kernel")
+    if m <= 0 or n <= 0:
+        return np.zeros(data.shape[:-2] + (max(m, 0), max(n, 0)), dtype=data.dtype)
+    # window (i, j) of the reference covers padded rows i+1 .. i+bi: centre i + 1 + bi//2
+    h = bi // 2
+    dev = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).cuda()
+    out, _, status = engine.neighbourhood(dev, h, method="square", sum_only=True)
+    engine.check_status(status)
+    res = out[..., 1 + h:1 + h + m, 1 + h:1 + h + n].cpu().numpy()
+    if issubclass(data.dtype.type, np.integer) or data.dtype == np.bool_:
+        return np.rint(res).astype(np.int64)
+    return res.astype(np.float64)

@@ -29,7 +29,7 @@ extern "C" {
 #define NBH_ABI_VERSION 1
 
 /* comparison operators, improver/utilities/probability_manipulation.py:15-66 */
-enum { NBH_OP_GT = 0, NBH_OP_GE = 1, NBH_OP_LT = 2, NBH_OP_LE = 3 };
+enum { NBH_OP_GT = 0, NBH_OP_GE = 1, NBH_OP_LT = 2, NBH_OP_LE = 3, NBH_OP_EQ = 4 };
 
 /* flags */
 enum {
