@@ -202,13 +202,154 @@ __global__ void circ_tables_kernel(double* ktab, int* wtab, float* area_const, i
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Large radii: the 2r+1-row prefix ring no longer fits in shared memory (and a
+// strip cannot even hold the 2r halo), so the float64 row prefixes of a batch
+// of planes are written to global memory once (they stay L2-resident: a UK
+// plane is 8 MB) and every output gathers 2 prefix values per kernel row.
+// ---------------------------------------------------------------------------
+struct CircGlobalParams {
+  const float* in;
+  float* out;
+  uint8_t* out_mask;
+  const uint8_t* mask2d;
+  const uint8_t* mask_nd;
+  const float* area;
+  const int* wtab;
+  double* prefix;        // [batch][ny][nx] inclusive row prefix of the member-summed, masked values
+  double* cprefix;       // MASKND: same for the valid mask
+  int32_t* status;
+  long long plane_stride, member_stride;
+  long long plane0;      // first plane of this batch
+  int n_batch;
+  int n_members, ny, nx, r;
+  int flags, n_thr, t;
+  double inv_members;
+  float area_const;
+  ThrDev thr;
+};
+
+// one warp per (plane, row): member sum + inclusive prefix along x
+__global__ void __launch_bounds__(256) circ_prefix_kernel(const CircGlobalParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long row_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row_id >= (long long)p.n_batch * p.ny) return;
+  const int b = (int)(row_id / p.ny), y = (int)(row_id % p.ny);
+  const long long plane = p.plane0 + b;
+  const float* in_row = p.in + plane * p.plane_stride + (long long)y * p.nx;
+  const uint8_t* mnd_row = p.mask_nd ? p.mask_nd + plane * p.plane_stride + (long long)y * p.nx : nullptr;
+  const uint8_t* m2_row = p.mask2d ? p.mask2d + (long long)y * p.nx : nullptr;
+  double* pre = p.prefix + ((long long)b * p.ny + y) * p.nx;
+  double* cpre = p.cprefix ? p.cprefix + ((long long)b * p.ny + y) * p.nx : nullptr;
+  double carry = 0.0, ccarry = 0.0;
+  float nanacc = 0.f;
+  for (int x0 = 0; x0 < p.nx; x0 += 32) {
+    const int x = x0 + lane;
+    float P = 0.f, okf = 0.f;
+    if (x < p.nx) {
+      const bool m2 = m2_row ? (m2_row[x] != 0) : true;
+      bool valid = m2, seen = true;
+      if (mnd_row) { seen = mnd_row[x] == 0; valid = valid && seen; }
+      for (int m = 0; m < p.n_members; ++m) {
+        const float d = __ldg(in_row + (long long)m * p.member_stride + x);
+        if (seen) nanacc = max_nan(nanacc, fabsf(d));
+        const float tv = p.thr.mode ? truth_value(d, p.thr) : d;
+        P += valid ? tv : 0.f;
+      }
+      okf = valid ? 1.f : 0.f;
+    }
+    double incl = (double)P, cincl = (double)okf;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double o = __shfl_up_sync(0xffffffffu, incl, d);
+      const double oc = __shfl_up_sync(0xffffffffu, cincl, d);
+      if (lane >= d) { incl += o; cincl += oc; }
+    }
+    if (x < p.nx) {
+      pre[x] = carry + incl;
+      if (cpre) cpre[x] = ccarry + cincl;
+    }
+    carry += __shfl_sync(0xffffffffu, incl, 31);
+    ccarry += __shfl_sync(0xffffffffu, cincl, 31);
+  }
+  if (__any_sync(0xffffffffu, __isnanf(nanacc)) && lane == 0)
+    atomicOr(reinterpret_cast<unsigned*>(p.status), 1u);
+}
+
+__device__ __forceinline__ double span_sum(const double* pre, int x, int w, int nx) {
+  const int lo = max(x - w, 0), hi = min(x + w, nx - 1);
+  double s = pre[hi] - (lo > 0 ? pre[lo - 1] : 0.0);
+  const int nl = lo - (x - w), nr = (x + w) - hi;     // replicated edge cells (mode="nearest")
+  if (nl > 0) s += (double)nl * pre[0];
+  if (nr > 0) s += (double)nr * (pre[nx - 1] - (nx > 1 ? pre[nx - 2] : 0.0));
+  return s;
+}
+
+__global__ void __launch_bounds__(256) circ_gather_kernel(const CircGlobalParams p) {
+  extern __shared__ int wtab_s[];
+  for (int k = threadIdx.x; k <= p.r; k += blockDim.x) wtab_s[k] = p.wtab[k];
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_plane = (long long)p.ny * p.nx;
+  if (i >= (long long)p.n_batch * per_plane) return;
+  const int b = (int)(i / per_plane);
+  const long long pt = i - (long long)b * per_plane;
+  const int y = (int)(pt / p.nx), x = (int)(pt % p.nx);
+  const double* pre = p.prefix + (long long)b * per_plane;
+  const double* cpre = p.cprefix ? p.cprefix + (long long)b * per_plane : nullptr;
+  double S = 0.0, A = 0.0;
+  for (int dy = -p.r; dy <= p.r; ++dy) {
+    const int w = wtab_s[dy < 0 ? -dy : dy];
+    const int ys = min(max(y + dy, 0), p.ny - 1);
+    S += span_sum(pre + (long long)ys * p.nx, x, w, p.nx);
+    if (cpre) A += span_sum(cpre + (long long)ys * p.nx, x, w, p.nx);
+  }
+  const long long plane = p.plane0 + b;
+  const long long o = (plane * p.n_thr + p.t) * per_plane + pt;
+  float res;
+  if (p.flags & NBH_SUM_ONLY) {
+    res = (float)S;
+  } else {
+    const float Af = cpre ? (float)A : (p.mask2d ? p.area[pt] : p.area_const);
+    res = (Af == 0.f) ? __int_as_float(0x7fc00000) : (float)(S / (double)Af * p.inv_members);
+  }
+  p.out[o] = res;
+  if (p.out_mask) {
+    bool masked = p.mask2d ? (p.mask2d[pt] == 0) : false;
+    if (p.mask_nd) masked = masked || (p.mask_nd[plane * p.plane_stride + pt] != 0);
+    p.out_mask[o] = masked ? 1 : 0;
+  }
+}
+
+// area_sum for an external mask at large radius, from the prefix of the mask itself
+__global__ void circ_mask_to_float_kernel(const uint8_t* mask, float* as_float, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) as_float[i] = mask[i] ? 1.f : 0.f;
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr int kCircSmemMaxRadius = 40;          // beyond this the global-prefix path is used
+constexpr size_t kCircPrefixBudget = 256u << 20;  // bytes of float64 prefixes per batch (L2-friendly)
+
+int env_int(const char* name, int dflt);
+// unweighted discs: global-prefix gather from radius NBH_CIRC_GLOBAL_MIN_R upwards
+static bool use_global_path(const NbhDesc& d) {
+  if (d.cells > kCircSmemMaxRadius) return true;
+  if (d.flags & NBH_WEIGHTED) return false;
+  return d.cells >= env_int("NBH_CIRC_GLOBAL_MIN_R", 7);   // measured crossover on B200 (profiles/)
+}
 
 struct CircWorkspace {
   double* ktab;
   int* wtab;
   float* area_const;
   float* area;
+  double* prefix;
+  double* cprefix;
+  float* maskf;
+  int batch;
   size_t total;
 };
 
@@ -220,6 +361,17 @@ static void carve(const NbhDesc& d, void* ws, CircWorkspace* w) {
   w->wtab = reinterpret_cast<int*>(base + off); off = align_up(off + (r + 1) * 4, 256);
   w->area_const = reinterpret_cast<float*>(base + off); off = align_up(off + 4, 256);
   w->area = reinterpret_cast<float*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 4, 256);
+  w->prefix = w->cprefix = nullptr; w->maskf = nullptr; w->batch = 0;
+  if (use_global_path(d)) {
+    const size_t per_plane = (size_t)d.ny * d.nx * 8;
+    long long batch = (long long)(kCircPrefixBudget / per_plane);
+    if (batch < 1) batch = 1;
+    if (batch > d.n_planes) batch = d.n_planes;
+    w->batch = (int)batch;
+    w->prefix = reinterpret_cast<double*>(base + off); off = align_up(off + per_plane * batch, 256);
+    if (d.mask_nd) { w->cprefix = reinterpret_cast<double*>(base + off); off = align_up(off + per_plane * batch, 256); }
+    w->maskf = reinterpret_cast<float*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 4, 256);
+  }
   w->total = off;
 }
 
@@ -262,6 +414,56 @@ int run_circular(const NbhDesc* d, const float* in, float* out, uint8_t* out_mas
   const int r = d->cells, nb = 2 * r + 1;
   CircWorkspace w;
   carve(*d, workspace, &w);
+
+  if (use_global_path(*d)) {
+    NBH_REQUIRE(!weighted, "weighted_mode is limited to radii of at most %d grid cells", kCircSmemMaxRadius);
+    CircGlobalParams g;
+    memset(&g, 0, sizeof(g));
+    ThrSet ts;
+    int tm = 0;
+    if (fill_thresholds(*d, &ts, &tm)) return 1;
+    g.in = in; g.out = out; g.out_mask = out_mask; g.mask2d = d->mask2d; g.mask_nd = d->mask_nd;
+    g.area = w.area; g.wtab = w.wtab; g.prefix = w.prefix; g.cprefix = w.cprefix; g.status = status;
+    g.plane_stride = d->plane_stride; g.member_stride = d->member_stride;
+    g.n_members = d->n_members; g.ny = d->ny; g.nx = d->nx; g.r = r; g.flags = d->flags;
+    g.n_thr = max(d->n_thresholds, 1);
+    g.inv_members = (d->flags & NBH_SUM_ONLY) ? 1.0 : 1.0 / (double)d->n_members;
+    {
+      double tot = 0.0;
+      for (int dy = -r; dy <= r; ++dy) tot += 2.0 * floor(sqrt((double)(r * r - dy * dy))) + 1.0;
+      g.area_const = (float)tot;
+    }
+    NBH_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int32_t), st));
+    circ_tables_kernel<<<1, 256, 0, st>>>(w.ktab, w.wtab, w.area_const, r, 0);
+    const long long npts = (long long)d->ny * d->nx;
+    const size_t gsm = (size_t)(r + 1) * 4;
+    if (d->mask2d && !masknd && !(d->flags & NBH_SUM_ONLY)) {
+      // area_sum = the same gather applied to the mask (one plane, sum_only)
+      circ_mask_to_float_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(d->mask2d, w.maskf, npts);
+      CircGlobalParams a = g;
+      a.in = w.maskf; a.out = w.area; a.out_mask = nullptr; a.mask2d = nullptr; a.mask_nd = nullptr;
+      a.cprefix = nullptr; a.plane_stride = npts; a.member_stride = 0; a.n_members = 1; a.n_thr = 1; a.t = 0;
+      a.plane0 = 0; a.n_batch = 1; a.flags = NBH_SUM_ONLY; a.thr.mode = 0;
+      circ_prefix_kernel<<<(unsigned)((d->ny + 7) / 8), 256, 0, st>>>(a);
+      circ_gather_kernel<<<(unsigned)((npts + 255) / 256), 256, gsm, st>>>(a);
+    }
+    ProfileScope prof(st);
+    for (int t = 0; t < g.n_thr; ++t) {
+      g.t = t;
+      g.thr = ts.t[d->n_thresholds ? t : 0];
+      if (!d->n_thresholds) g.thr.mode = 0;
+      for (long long p0 = 0; p0 < d->n_planes; p0 += w.batch) {
+        g.plane0 = p0;
+        g.n_batch = (int)min((long long)w.batch, d->n_planes - p0);
+        const long long rows = (long long)g.n_batch * d->ny;
+        circ_prefix_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(g);
+        const long long outs = (long long)g.n_batch * npts;
+        circ_gather_kernel<<<(unsigned)((outs + 255) / 256), 256, gsm, st>>>(g);
+      }
+    }
+    NBH_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
 
   int dev = 0, smem_max = 0;
   cudaGetDevice(&dev);

@@ -178,3 +178,41 @@ def test_threshold_collapse_with_masks_vs_oracle():
     np.testing.assert_array_equal(cnt.cpu().numpy(), contrib.astype(np.int32))
     np.testing.assert_array_equal(out.cpu().numpy(), exp)      # same float32 accumulation order
     assert inv is not None and inv[5, 5]
+
+
+@pytest.mark.parametrize("masked_input", [False, True])
+def test_circular_large_radius_global_prefix_path(masked_input):
+    """Radii beyond the shared-memory ring (config 2: 162 km = 81 cells) use the
+    global row-prefix gather; checked here at r=45 on a small grid."""
+    from improver_b200 import engine
+
+    rng = np.random.default_rng(21)
+    shape, cells = (97, 120), 45
+    data = rng.random((2,) + shape).astype(np.float32)
+    data[1, 10:30, 40:60] = 0.0
+    mask = (rng.random(shape) < 0.7).astype(np.uint8)
+    inmask = rng.random(data.shape) < 0.2 if masked_input else None
+    for m in (None, mask):
+        for sum_only in (False, True):
+            out, omask, status = engine.neighbourhood(
+                _dev(data), cells, method="circular", mask2d=_dev(m) if m is not None else None,
+                mask_nd=_dev(inmask.astype(np.uint8)) if inmask is not None else None,
+                sum_only=sum_only, want_mask=True)
+            engine.check_status(status)
+            exp = np.stack([np.ma.getdata(orc.neighbourhood(
+                np.ma.masked_array(data[i], inmask[i]) if inmask is not None else data[i], m,
+                method="circular", cells=cells, sum_only=sum_only, re_mask=False)) for i in range(2)])
+            scale = max(1.0, float(np.nanmax(np.abs(exp)))) if sum_only else 1.0
+            _assert_close(out.cpu().numpy(), exp, atol=ATOL * scale)
+
+
+def test_fused_circular_large_radius():
+    from improver_b200 import engine
+
+    rng = np.random.default_rng(22)
+    data = rng.gamma(2.0, 1.5, (3, 2, 90, 100)).astype(np.float32)
+    exp = orc.threshold_square_mean(data, [2.0], [(1.4, 2.6)], ">", 42, method="circular")
+    out, _, status = engine.neighbourhood(_dev(data), 42, method="circular",
+                                          thresholds=[(2.0, 1.4, 2.6, ">")], collapse_members=True)
+    engine.check_status(status)
+    _assert_close(out.cpu().numpy(), exp)
