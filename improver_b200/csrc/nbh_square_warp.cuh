@@ -25,6 +25,8 @@ __device__ __forceinline__ const float* byte_offset(const float* base, unsigned 
   return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + bytes);
 }
 
+constexpr int kSqHrowRows = 8;        // prefix rows per warp (rows mode batches up to 8 horizontal passes)
+
 struct SqWarpGeom {
   int WS;        // columns loaded per warp (32 * VEC * groups)
   int W0, W;     // output columns of strip 0 / of the other strips
@@ -43,10 +45,10 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
   // block-shared reciprocal table, then warp-private ring + prefix row
   double* rtab = reinterpret_cast<double*>(smem_raw);                        // [nb + 2]
   const size_t rtab_elems = (size_t)((nb + 2) & ~1);
-  const size_t per_warp = (size_t)(WS + 2) * 8 + (size_t)nb * WS * 4;
+  const size_t per_warp = (size_t)(WS + 2) * 8 * kSqHrowRows + (size_t)nb * WS * 4;
   unsigned char* wbase = smem_raw + rtab_elems * 8 + (size_t)warp * per_warp;
-  double* hrow = reinterpret_cast<double*>(wbase);                           // [WS + 1]
-  float* ring = reinterpret_cast<float*>(wbase + (size_t)(WS + 2) * 8);       // [nb][WS]
+  double* hrow = reinterpret_cast<double*>(wbase);                           // [rows][WS + 2]
+  float* ring = reinterpret_cast<float*>(wbase + (size_t)(WS + 2) * 8 * kSqHrowRows);   // [nb][WS]
 
   for (int k = threadIdx.x + 1; k <= nb; k += blockDim.x) rtab[k] = 1.0 / (double)k;
   __syncthreads();     // the only block-level barrier in the kernel
@@ -99,7 +101,7 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) ring[s * WS + c0[g2] + v] = 0.f;
   }
-  if (lane == 0) hrow[0] = 0.0;
+  if (lane < kSqHrowRows) hrow[lane * (WS + 2)] = 0.0;
   __syncwarp();
 
   double V[G][VEC];
@@ -128,7 +130,8 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
   int ik = 0, ichunk = 0, ck = 0, cchunk = 0;
 
   // ---- one finished input row: ring, vertical sums, horizontal pass, store ----
-  auto finish_row = [&](int k, bool row_in_dom) {
+  // vertical part: push the finished member-summed row through the ring
+  auto vertical = [&](bool row_in_dom) {
 #pragma unroll
     for (int g2 = 0; g2 < G; ++g2)
 #pragma unroll
@@ -143,17 +146,17 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
         P[g2][v] = 0.f;
       }
     slot = (slot + 1 == nb) ? 0 : slot + 1;
-    if (k < 2 * r) return;                               // window not complete yet
-    const int yo = y_first + dir * (k - r);              // centre row of the window
-    // float64 inclusive prefix over the strip: lane-local, warp scan per group, group carry
-    __syncwarp();                                        // previous row's readers are done
+  };
+  // horizontal part 1: float64 inclusive prefix of the strip into a warp-private row
+  // (lane-local sums, warp-shuffle scan per group, carry between groups)
+  auto h_scan = [&](const double (&Vr)[G][VEC], double* hr) {
     double carry = 0.0;
 #pragma unroll
     for (int g2 = 0; g2 < G; ++g2) {
       double loc[VEC];
       double s = 0.0;
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) { s += V[g2][v]; loc[v] = s; }
+      for (int v = 0; v < VEC; ++v) { s += Vr[g2][v]; loc[v] = s; }
       double incl = s;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -162,10 +165,13 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
       }
       const double excl = carry + incl - s;
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) hrow[c0[g2] + v + 1] = excl + loc[v];
+      for (int v = 0; v < VEC; ++v) hr[c0[g2] + v + 1] = excl + loc[v];
       if (g2 + 1 < G) carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    __syncwarp();
+  };
+  // horizontal part 2: window sum = prefix difference, normalise, store
+  auto h_store = [&](int k, const double* hr) {
+    const int yo = y_first + dir * (k - r);              // centre row of the window
     const int rows_in = min(yo + r, p.ny - 1) - max(yo - r, 0) + 1;
     const double rrow = rtab[rows_in] * p.inv_members;
 #pragma unroll
@@ -177,7 +183,7 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
           const int cc = c0[g2] + v;
-          const double S = hrow[cc + r + 1] - hrow[max(cc - r, 0)];
+          const double S = hr[cc + r + 1] - hr[max(cc - r, 0)];
           if (sum_only) {
             o[v] = (float)S;
           } else if (M2D) {
@@ -196,6 +202,15 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
         }
       }
     }
+  };
+  // one finished input row, members mode (one row per chunk)
+  auto finish_row = [&](int k, bool row_in_dom) {
+    vertical(row_in_dom);
+    if (k < 2 * r) return;                               // window not complete yet
+    __syncwarp();                                        // previous row's readers are done
+    h_scan(V, hrow);
+    __syncwarp();
+    h_store(k, hrow);
   };
 
   // ---- edge-band bookkeeping for the trimming fix-up ----
@@ -276,6 +291,11 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
 
   auto consume = [&](float (&buf)[MB][G][VEC], unsigned (&mk)[MKN][G]) {
     if (ROWS) {
+      // The MB rows of a chunk are pushed through the vertical sums one after the
+      // other, but their horizontal passes are independent: snapshot V per row and
+      // run the MB scans together (instruction-level parallelism hides the shuffle
+      // latency that dominates when there is only one member per row).
+      double Vs[MB][G][VEC];
 #pragma unroll
       for (int j = 0; j < MB; ++j) {
         const int k = ck + j;
@@ -296,9 +316,21 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
 #pragma unroll
             for (int g2 = 0; g2 < G; ++g2) accumulate(buf[j][g2], M2D ? mk[j][g2] : 0u, P[g2], false, 0u, nel);
           }
-          finish_row(k, in_dom);
+          vertical(in_dom);
         }
+#pragma unroll
+        for (int g2 = 0; g2 < G; ++g2)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) Vs[j][g2][v] = V[g2][v];
       }
+      __syncwarp();                                      // previous chunk's readers are done
+#pragma unroll
+      for (int j = 0; j < MB; ++j)
+        if (ck + j < n_rows && ck + j >= 2 * r) h_scan(Vs[j], hrow + j * (WS + 2));
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < MB; ++j)
+        if (ck + j < n_rows && ck + j >= 2 * r) h_store(ck + j, hrow + j * (WS + 2));
       ck += MB;
     } else {
       if (ck < n_rows) {
@@ -370,7 +402,8 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
 
 inline size_t sq_warp_smem_bytes(int vec, int groups, int nb) {
   const int WS = 32 * vec * groups;
-  return (size_t)((nb + 2) & ~1) * 8 + (size_t)kSqWarpsPerBlock * ((size_t)(WS + 2) * 8 + (size_t)nb * WS * 4);
+  return (size_t)((nb + 2) & ~1) * 8 +
+         (size_t)kSqWarpsPerBlock * ((size_t)(WS + 2) * 8 * kSqHrowRows + (size_t)nb * WS * 4);
 }
 
 template <int VEC>
@@ -391,7 +424,8 @@ static int launch_square_warp_one(const SqParams& p, const SqWarpGeom& g, cudaSt
 // 36 floats per register buffer: MB * G * VEC == 36 (members mode), 16 (rows mode)
 template <int VEC, int G, int TM, bool M2D>
 static int launch_square_warp_mode(const SqParams& p, const SqWarpGeom& g, cudaStream_t st) {
-  constexpr int MBR = 16 / (VEC * G) > 0 ? 16 / (VEC * G) : 1;
+  constexpr int MBR0 = 16 / (VEC * G) > 0 ? 16 / (VEC * G) : 1;
+  constexpr int MBR = MBR0 > kSqHrowRows ? kSqHrowRows : MBR0;
   constexpr int MBM = 36 / (VEC * G) > 18 ? 18 : 36 / (VEC * G);
   if (p.n_members == 1) return launch_square_warp_one<VEC, G, TM, M2D, true, true, MBR>(p, g, st);
   if (p.n_members % MBM == 0) return launch_square_warp_one<VEC, G, TM, M2D, false, true, MBM>(p, g, st);

@@ -16,7 +16,7 @@ struct ThrParams {
   ThrSet thr;
 };
 
-template <int VEC>
+template <int VEC, int TM>
 __global__ void __launch_bounds__(256) threshold_kernel(const ThrParams p) {
   const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (i0 >= p.n_points) return;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) threshold_kernel(const ThrParams p) {
       cnt[v] += 1;
 #pragma unroll
       for (int t = 0; t < kMaxThresholds; ++t)
-        if (t < T) acc[t][v] = __fadd_rn(acc[t][v], truth_value(d[v], p.thr.t[t]));
+        if (t < T) acc[t][v] = __fadd_rn(acc[t][v], truth_value_t<TM>(d[v], p.thr.t[t]));
     }
   }
   if (__isnanf(nanacc)) atomicOr(reinterpret_cast<unsigned*>(p.status), 1u);
@@ -71,21 +71,38 @@ int run_threshold(const float* in, const uint8_t* mask_nd, float* out, int32_t* 
   NBH_REQUIRE(n_thresholds >= 1 && n_thresholds <= kMaxThresholds, "n_thresholds must be in [1, %d]",
               kMaxThresholds);
   NBH_REQUIRE(n_collapse >= 1 && n_points >= 1, "empty input");
-  ThrParams p;
-  memset(&p, 0, sizeof(p));
-  p.thr.n = n_thresholds;
-  for (int i = 0; i < n_thresholds; ++i)
-    if (make_thr_dev(thresholds[i], &p.thr.t[i], mask_nd != nullptr)) return 1;
-  p.in = in; p.mask_nd = mask_nd; p.out = out; p.contrib = contrib; p.status = status;
-  p.n_collapse = n_collapse; p.n_points = n_points;
   NBH_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int32_t), st));
   const bool al16 = (n_points % 4 == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                     (!mask_nd || (uintptr_t)mask_nd % 4 == 0);
-  if (al16) {
-    const long long th = n_points / 4;
-    threshold_kernel<4><<<(unsigned)((th + 255) / 256), 256, 0, st>>>(p);
-  } else {
-    threshold_kernel<1><<<(unsigned)((n_points + 255) / 256), 256, 0, st>>>(p);
+  // one launch per run of thresholds sharing an evaluation mode (the kernel is
+  // specialised on it: deterministic compare / fuzzy float32 / fuzzy numpy.ma)
+  int t0 = 0;
+  while (t0 < n_thresholds) {
+    ThrParams p;
+    memset(&p, 0, sizeof(p));
+    int n = 0, mode = 0;
+    for (int i = t0; i < n_thresholds; ++i) {
+      ThrDev d;
+      if (make_thr_dev(thresholds[i], &d, mask_nd != nullptr)) return 1;
+      if (n == 0) mode = d.mode;
+      if (d.mode != mode) break;
+      p.thr.t[n++] = d;
+    }
+    p.thr.n = n;
+    p.in = in; p.mask_nd = mask_nd; p.out = out + (long long)t0 * n_points; p.contrib = contrib;
+    p.status = status; p.n_collapse = n_collapse; p.n_points = n_points;
+    const long long th = al16 ? n_points / 4 : n_points;
+    const unsigned blocks = (unsigned)((th + 255) / 256);
+    if (al16) {
+      if (mode == 1) threshold_kernel<4, 1><<<blocks, 256, 0, st>>>(p);
+      else if (mode == 2) threshold_kernel<4, 2><<<blocks, 256, 0, st>>>(p);
+      else threshold_kernel<4, 3><<<blocks, 256, 0, st>>>(p);
+    } else {
+      if (mode == 1) threshold_kernel<1, 1><<<blocks, 256, 0, st>>>(p);
+      else if (mode == 2) threshold_kernel<1, 2><<<blocks, 256, 0, st>>>(p);
+      else threshold_kernel<1, 3><<<blocks, 256, 0, st>>>(p);
+    }
+    t0 += n;
   }
   NBH_CHECK_CUDA(cudaGetLastError());
   return 0;
