@@ -16,20 +16,22 @@ struct ThrParams {
   ThrSet thr;
 };
 
-template <int VEC, int TM>
+template <int VEC, int TM, int T>
 __global__ void __launch_bounds__(256) threshold_kernel(const ThrParams p) {
   const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (i0 >= p.n_points) return;
-  float acc[kMaxThresholds][VEC];
+  float acc[T][VEC];
   int cnt[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
     cnt[v] = 0;
 #pragma unroll
-    for (int t = 0; t < kMaxThresholds; ++t) acc[t][v] = 0.f;
+    for (int t = 0; t < T; ++t) acc[t][v] = 0.f;
   }
   float nanacc = 0.f;
-  const int T = p.thr.n;
+  ThrDev thr[T];                                 // keep the threshold constants in registers
+#pragma unroll
+  for (int t = 0; t < T; ++t) thr[t] = p.thr.t[t];
   for (long long c = 0; c < p.n_collapse; ++c) {
     float d[VEC];
     uint8_t m[VEC];
@@ -43,25 +45,46 @@ __global__ void __launch_bounds__(256) threshold_kernel(const ThrParams p) {
       nanacc = max_nan(nanacc, fabsf(d[v]));
       cnt[v] += 1;
 #pragma unroll
-      for (int t = 0; t < kMaxThresholds; ++t)
-        if (t < T) acc[t][v] = __fadd_rn(acc[t][v], truth_value_t<TM>(d[v], p.thr.t[t]));
+      for (int t = 0; t < T; ++t) acc[t][v] = __fadd_rn(acc[t][v], truth_value_t<TM>(d[v], thr[t]));
     }
   }
   if (__isnanf(nanacc)) atomicOr(reinterpret_cast<unsigned*>(p.status), 1u);
 #pragma unroll
-  for (int t = 0; t < kMaxThresholds; ++t) {
-    if (t < T) {
-      float o[VEC];
+  for (int t = 0; t < T; ++t) {
+    float o[VEC];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v)   // np.divide(float32, int64) -> float64 -> float32 store
-        o[v] = cnt[v] ? (float)((double)acc[t][v] / (double)cnt[v]) : 0.f;
-      VecLoad<VEC>::st(p.out + (long long)t * p.n_points + i0, o);
+    for (int v = 0; v < VEC; ++v) {
+      // np.divide(float32, int64) -> float64 -> float32 store; a count of 1 (no
+      // collapse) is the identity
+      o[v] = cnt[v] > 1 ? (float)((double)acc[t][v] / (double)cnt[v]) : (cnt[v] ? acc[t][v] : 0.f);
     }
+    VecLoad<VEC>::st(p.out + (long long)t * p.n_points + i0, o);
   }
   if (p.contrib) {
 #pragma unroll
     for (int v = 0; v < VEC; ++v) p.contrib[i0 + v] = cnt[v];
   }
+}
+
+template <int VEC, int TM>
+static void launch_threshold_t(const ThrParams& p, int n, unsigned blocks, cudaStream_t st) {
+  switch (n) {
+    case 1: threshold_kernel<VEC, TM, 1><<<blocks, 256, 0, st>>>(p); break;
+    case 2: threshold_kernel<VEC, TM, 2><<<blocks, 256, 0, st>>>(p); break;
+    case 3: threshold_kernel<VEC, TM, 3><<<blocks, 256, 0, st>>>(p); break;
+    case 4: threshold_kernel<VEC, TM, 4><<<blocks, 256, 0, st>>>(p); break;
+    case 5: threshold_kernel<VEC, TM, 5><<<blocks, 256, 0, st>>>(p); break;
+    case 6: threshold_kernel<VEC, TM, 6><<<blocks, 256, 0, st>>>(p); break;
+    case 7: threshold_kernel<VEC, TM, 7><<<blocks, 256, 0, st>>>(p); break;
+    default: threshold_kernel<VEC, TM, 8><<<blocks, 256, 0, st>>>(p); break;
+  }
+}
+
+template <int VEC>
+static void launch_threshold(const ThrParams& p, int mode, int n, unsigned blocks, cudaStream_t st) {
+  if (mode == 1) launch_threshold_t<VEC, 1>(p, n, blocks, st);
+  else if (mode == 2) launch_threshold_t<VEC, 2>(p, n, blocks, st);
+  else launch_threshold_t<VEC, 3>(p, n, blocks, st);
 }
 
 int run_threshold(const float* in, const uint8_t* mask_nd, float* out, int32_t* contrib,
@@ -93,15 +116,8 @@ int run_threshold(const float* in, const uint8_t* mask_nd, float* out, int32_t* 
     p.status = status; p.n_collapse = n_collapse; p.n_points = n_points;
     const long long th = al16 ? n_points / 4 : n_points;
     const unsigned blocks = (unsigned)((th + 255) / 256);
-    if (al16) {
-      if (mode == 1) threshold_kernel<4, 1><<<blocks, 256, 0, st>>>(p);
-      else if (mode == 2) threshold_kernel<4, 2><<<blocks, 256, 0, st>>>(p);
-      else threshold_kernel<4, 3><<<blocks, 256, 0, st>>>(p);
-    } else {
-      if (mode == 1) threshold_kernel<1, 1><<<blocks, 256, 0, st>>>(p);
-      else if (mode == 2) threshold_kernel<1, 2><<<blocks, 256, 0, st>>>(p);
-      else threshold_kernel<1, 3><<<blocks, 256, 0, st>>>(p);
-    }
+    if (al16) launch_threshold<4>(p, mode, n, blocks, st);
+    else launch_threshold<1>(p, mode, n, blocks, st);
     t0 += n;
   }
   NBH_CHECK_CUDA(cudaGetLastError());
