@@ -12,7 +12,7 @@
 // columns, no synchronisation), and (3) per output row does the horizontal
 // window sum as a difference of a float64 row prefix built with a warp-shuffle
 // scan, normalises by the valid-cell count and stores float32.
-#include "nbh_square_warp.cuh"
+#include "nbh_square_tma.cuh"
 
 namespace nbh {
 
@@ -330,11 +330,16 @@ static bool plan_square_warp(const NbhDesc& d, int vec, SqWarpGeom* g) {
   return true;
 }
 
+bool make_square_tensor_map(const float* in, int ny, int nx, long long n_planes, int n_members,
+                            long long plane_stride, long long member_stride, int box_cols, CUtensorMap* map,
+                            int* super_rows);
+
 struct SqWorkspace {
   unsigned* edge_flags;
   SliceStats* stats;
   int* suspects;
   int* n_suspects;
+  CUtensorMap* tmap;
   double* rcp_count;
   uint16_t* tmp;
   size_t total;
@@ -348,6 +353,7 @@ static void carve_workspace(const NbhDesc& d, void* ws, SqWorkspace* w) {
   w->stats = reinterpret_cast<SliceStats*>(base + off); off = align_up(off + nslices * sizeof(SliceStats), 256);
   w->suspects = reinterpret_cast<int*>(base + off); off = align_up(off + nslices * 4, 256);
   w->n_suspects = reinterpret_cast<int*>(base + off); off = align_up(off + 4, 256);
+  w->tmap = reinterpret_cast<CUtensorMap*>(base + off); off = align_up(off + sizeof(CUtensorMap), 256);
   w->rcp_count = reinterpret_cast<double*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 8, 256);
   w->tmp = reinterpret_cast<uint16_t*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 2, 256);
   w->total = off;
@@ -435,7 +441,37 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   int rc;
   SqWarpGeom wg;
   const bool use_warp = !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && plan_square_warp(*d, pl.vec, &wg);
-  if (use_warp) {
+  // TMA-fed variant: fused member path on grids whose rows (or row pairs) are 16-byte multiples
+  bool use_tma = false;
+  CUtensorMap tmap;
+  SqTmaGeom tg;
+  if (use_warp && pl.vec >= 2 && d->n_members >= 2 && d->n_members <= 32 && !(d->flags & NBH_WRAP_X) &&
+      env_int("NBH_SQ_TMA", 0)) {   // opt-in: measured 0.61 ms vs 0.57 ms for the register-pipelined kernel
+    SqWarpGeom wg2;
+    if (plan_square_warp(*d, 2, &wg2)) {          // the TMA kernel works on 2-column lane groups
+      int super = 0;
+      if (make_square_tensor_map(in, d->ny, d->nx, d->n_planes, d->n_members, d->plane_stride, d->member_stride,
+                                 wg2.WS + 4, &tmap, &super)) {
+        tg.super_rows = super;
+        tg.box_cols = wg2.WS + 4;
+        tg.stage_floats = sq_tma_stage_floats(wg2.WS, d->n_members);
+        const size_t fixed = sq_tma_smem_bytes(wg2.WS, p.nb, d->n_members, 0);
+        const size_t budget = (size_t)env_int("NBH_SQ_TMA_SMEM", 26 * 1024);
+        int stages = (int)((budget > fixed ? budget - fixed : 0) / ((size_t)tg.stage_floats * 4));
+        stages = env_int("NBH_SQ_TMA_STAGES", stages);
+        if (stages >= 2) {
+          tg.n_stages = min(stages, 8);
+          wg = wg2;
+          use_tma = true;
+        }
+      }
+    }
+  }
+  if (use_tma) {
+    NBH_CHECK_CUDA(cudaMemcpyAsync(w.tmap, &tmap, sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+    ProfileScope prof(st);
+    rc = launch_square_tma(p, wg, tg, w.tmap, tm, d->mask2d != nullptr, st);
+  } else if (use_warp) {
     ProfileScope prof(st);
     const bool m2d = d->mask2d != nullptr;
     switch (pl.vec) {

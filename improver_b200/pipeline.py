@@ -24,12 +24,26 @@ def pinned_like(t: torch.Tensor) -> torch.Tensor:
     return torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
 
 
+_pinned_out_cache = {}
+
+
+def _pinned_out(shape):
+    """Pinned result buffers are expensive to allocate (cudaHostAlloc): keep one per shape."""
+    buf = _pinned_out_cache.get(shape)
+    if buf is None:
+        buf = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        _pinned_out_cache[shape] = buf
+    return buf
+
+
 def threshold_neighbourhood_mean_host(host_in, thresholds: Sequence[float], bounds, comparison: str,
                                       cells: int, method: str = "square", mask2d=None,
-                                      chunk_leads: int = 6, device=None):
+                                      chunk_leads: int = 6, device=None, out=None):
     """Fuzzy threshold -> neighbourhood -> realization mean for a HOST cube.
 
     host_in   float32 (R, L, ny, nx) numpy array or (preferably pinned) CPU tensor
+    out       optional pinned float32 (L, T, ny, nx) CPU tensor to receive the result;
+              by default a cached pinned buffer is returned (overwritten by the next call)
     returns   float32 (L, T, ny, nx) pinned CPU tensor
     Raises ValueError("Error: NaN detected in input cube data") like the
     reference plugins (nbhood.py:167-168)."""
@@ -41,14 +55,17 @@ def threshold_neighbourhood_mean_host(host_in, thresholds: Sequence[float], boun
     R, L, ny, nx = (int(s) for s in host_in.shape)
     T = len(thresholds)
     thr = [(t, b[0], b[1], comparison) for t, b in zip(thresholds, bounds)]
-    out_host = torch.empty((L, T, ny, nx), dtype=torch.float32, pin_memory=True)
+    out_host = out if out is not None else _pinned_out((L, T, ny, nx))
+    if tuple(out_host.shape) != (L, T, ny, nx) or out_host.dtype != torch.float32 or out_host.is_cuda:
+        raise ValueError("out must be a float32 CPU tensor of shape (L, T, ny, nx)")
     m2 = None
     if mask2d is not None:
         m2 = torch.as_tensor(np.asarray(mask2d) != 0).to(torch.uint8).to(dev)
     chunk = max(c for c in range(1, max(1, min(chunk_leads, L)) + 1) if L % c == 0)
     bufs = [torch.empty((R, chunk, ny, nx), dtype=torch.float32, device=dev) for _ in range(2)]
     outs = [torch.empty((chunk, T, ny, nx), dtype=torch.float32, device=dev) for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
+    copy_stream = torch.cuda.Stream(device=dev)      # host -> device
+    back_stream = torch.cuda.Stream(device=dev)      # device -> host (own DMA engine, own queue)
     compute = torch.cuda.current_stream(dev)
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
@@ -71,12 +88,13 @@ def threshold_neighbourhood_mean_host(host_in, thresholds: Sequence[float], boun
                                         collapse_members=True, out=outs[b])
         statuses.append(st)
         consumed[b].record(compute)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[b])
+        with torch.cuda.stream(back_stream):
+            back_stream.wait_event(consumed[b])
             out_host[l0:l1].copy_(outs[b], non_blocking=True)
-            drained[b].record(copy_stream)
+            drained[b].record(back_stream)
     status = torch.stack(statuses).amax(dim=0)
     compute.wait_stream(copy_stream)
+    compute.wait_stream(back_stream)
     engine.check_status(status)          # D2H read of the status words: synchronises
     torch.cuda.current_stream(dev).synchronize()
     return out_host

@@ -216,3 +216,22 @@ def test_fused_circular_large_radius():
                                           thresholds=[(2.0, 1.4, 2.6, ">")], collapse_members=True)
     engine.check_status(status)
     _assert_close(out.cpu().numpy(), exp)
+
+
+@pytest.mark.parametrize("shape", [(3, 2, 64, 96), (4, 2, 50, 98)])
+def test_tma_variant_matches_oracle(shape, monkeypatch):
+    """The TMA-fed variant of the fused square kernel (opt-in, NBH_SQ_TMA=1):
+    plain-row tensor map (nx % 4 == 0) and the two-rows-per-tensor-row map
+    (nx % 4 == 2, 16-byte aligned box starts)."""
+    from improver_b200 import engine
+
+    monkeypatch.setenv("NBH_SQ_TMA", "1")
+    rng = np.random.default_rng(31)
+    data = rng.gamma(2.0, 1.5, shape).astype(np.float32)
+    mask = (rng.random(shape[2:]) < 0.8).astype(np.uint8)
+    for m in (None, mask):
+        exp = orc.threshold_square_mean(data, [2.0], [(1.4, 2.6)], ">", 3, mask=m)
+        out, _, status = engine.neighbourhood(_dev(data), 3, mask2d=_dev(m) if m is not None else None,
+                                              thresholds=[(2.0, 1.4, 2.6, ">")], collapse_members=True)
+        engine.check_status(status)
+        _assert_close(out.cpu().numpy(), exp)
