@@ -136,6 +136,16 @@ int make_thr_dev(const NbhThreshold& h, ThrDev* d, bool ma_arith) {
   const bool invert = (h.op == NBH_OP_LT || h.op == NBH_OP_LE);
   d->fs_lo = invert ? -d->rcph_lo : d->rcph_lo;
   d->fs_hi = invert ? -d->rcph_hi : d->rcph_hi;
+  // symmetric bounds (fuzzy_factor): one slope serves both sides of the threshold
+  d->fast_kind = 2;
+  const double s_lo = 0.5 / (double)d->den_lo, s_hi = 0.5 / (double)d->den_hi;
+  if (std::fabs(s_lo - s_hi) <= 2e-7 * std::fmax(s_lo, s_hi)) {
+    const double s1 = 0.5 * (s_lo + s_hi) * (invert ? -1.0 : 1.0);
+    d->fs1 = (float)s1;
+    d->fc1 = (float)(0.5 - (double)d->thr * (double)d->fs1);
+    const double mag = std::fmax(std::fabs((double)d->hi * s1), std::fabs((double)d->lo * s1));
+    d->fast_kind = (std::fmax(mag, std::fabs((double)d->fc1)) <= 8.0) ? 5 : 4;
+  }
   find_one_interval(d);
   return 0;
 }

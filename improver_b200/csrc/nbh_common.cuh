@@ -47,6 +47,8 @@ struct ThrDev {
   double lo64;    // bounds[0] unrounded (np.ma arithmetic promotes to float64)
   // branch-free evaluation used inside the neighbourhood sums (truth_value_fast)
   float fs_lo, fs_hi;   // +-0.5/den_lo, +-0.5/den_hi (negated for "less than" comparisons)
+  float fs1, fc1;       // single-slope forms (symmetric bounds): sat((d-thr)*fs1 + .5), sat(d*fs1 + fc1)
+  int fast_kind;        // 2 general, 4 single slope, 5 single slope + single FMA
   // exact "truth value == 1" test on the data itself (edge-band flags of the
   // trimming fix-up): one_lo <= d <= one_hi  <=>  truth_value(d) == 1.0f
   float one_lo, one_hi;
@@ -133,11 +135,17 @@ __device__ __forceinline__ bool truth_not_one(float d, const ThrDev& p) {
   return !(d >= p.one_lo && d <= p.one_hi);
 }
 
-// TM codes of the neighbourhood kernels: 0 raw, 1 compare, 2 fuzzy, 3 fuzzy np.ma
+// TM codes of the neighbourhood kernels: 0 raw, 1 compare, 2 fuzzy, 3 fuzzy np.ma,
+// 4 / 5 fuzzy with symmetric bounds (fuzzy_factor): below and above the
+// threshold the membership has the same slope (up to float32 rounding of the
+// two denominators), so the sign select disappears: 2 instructions (4) or a
+// single saturating FMA (5, when |d*slope| stays small enough for 5e-7 accuracy)
 template <int TM>
 __device__ __forceinline__ float truth_value_sum(float d, const ThrDev& p) {
   if (TM == 2) return truth_value_fast(d, p);
-  return truth_value_t<TM>(d, p);
+  if (TM == 4) return __saturatef(__fmaf_rn(__fsub_rn(d, p.thr), p.fs1, 0.5f));
+  if (TM == 5) return __saturatef(__fmaf_rn(d, p.fs1, p.fc1));
+  return truth_value_t<TM == 4 || TM == 5 ? 2 : TM>(d, p);
 }
 
 // runtime-dispatched form (un-fused threshold kernel, fix-up kernels)

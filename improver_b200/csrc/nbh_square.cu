@@ -441,6 +441,13 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   int rc;
   SqWarpGeom wg;
   const bool use_warp = !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && plan_square_warp(*d, pl.vec, &wg);
+  // fuzzy launches: pick the cheapest membership form every threshold of the launch supports
+  int tm_warp = tm;
+  if (tm == 2 && !masknd && env_int("NBH_SQ_FASTKIND", 1)) {
+    int kind = 5;
+    for (int i = 0; i < d->n_thresholds; ++i) kind = min(kind, p.thr.t[i].fast_kind == 2 ? 2 : p.thr.t[i].fast_kind);
+    tm_warp = kind;
+  }
   // TMA-fed variant: fused member path on grids whose rows (or row pairs) are 16-byte multiples
   bool use_tma = false;
   CUtensorMap tmap;
@@ -475,9 +482,9 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
     ProfileScope prof(st);
     const bool m2d = d->mask2d != nullptr;
     switch (pl.vec) {
-      case 4: rc = launch_square_warp_vec<4>(p, wg, tm, m2d, st); break;
-      case 2: rc = launch_square_warp_vec<2>(p, wg, tm, m2d, st); break;
-      default: rc = launch_square_warp_vec<1>(p, wg, tm, m2d, st); break;
+      case 4: rc = launch_square_warp_vec<4>(p, wg, tm_warp, m2d, st); break;
+      case 2: rc = launch_square_warp_vec<2>(p, wg, tm_warp, m2d, st); break;
+      default: rc = launch_square_warp_vec<1>(p, wg, tm_warp, m2d, st); break;
     }
   } else {
     ProfileScope prof(st);

@@ -450,7 +450,12 @@ static int launch_square_warp_groups(const SqParams& p, const SqWarpGeom& g, cud
       case 2: return launch_square_warp_groups<VEC, 1, false>(p, g, st);                               \
       case 3: return launch_square_warp_groups<VEC, 1, true>(p, g, st);                                \
       case 4: return launch_square_warp_groups<VEC, 2, false>(p, g, st);                               \
-      default: return launch_square_warp_groups<VEC, 2, true>(p, g, st);                               \
+      case 5: return launch_square_warp_groups<VEC, 2, true>(p, g, st);                                \
+      case 8: return launch_square_warp_groups<VEC, 4, false>(p, g, st);                               \
+      case 9: return launch_square_warp_groups<VEC, 4, true>(p, g, st);                                \
+      case 10: return launch_square_warp_groups<VEC, 5, false>(p, g, st);                              \
+      case 11: return launch_square_warp_groups<VEC, 5, true>(p, g, st);                               \
+      default: nbh::set_error("unsupported warp kernel variant"); return 1;                            \
     }                                                                                                \
   }
 
