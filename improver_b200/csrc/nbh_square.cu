@@ -455,20 +455,36 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   if (use_warp && pl.vec >= 2 && d->n_members >= 2 && d->n_members <= 32 && !(d->flags & NBH_WRAP_X) &&
       env_int("NBH_SQ_TMA", 0)) {   // opt-in: measured 0.61 ms vs 0.57 ms for the register-pipelined kernel
     SqWarpGeom wg2;
-    if (plan_square_warp(*d, 2, &wg2)) {          // the TMA kernel works on 2-column lane groups
+    if (plan_square_warp(*d, 2, &wg2) && wg2.WS == 64 && d->nx >= kTmaWarps * wg2.W) {
+      // block tiles: kTmaWarps windows per block; the first block strip has no left halo
+      const int Wb = kTmaWarps * wg2.W, W0b = Wb + wg2.hl;
+      const int n_bstrips = 1 + (d->nx > W0b ? (d->nx - W0b + Wb - 1) / Wb : 0);
       int super = 0;
-      if (make_square_tensor_map(in, d->ny, d->nx, d->n_planes, d->n_members, d->plane_stride, d->member_stride,
-                                 wg2.WS + 4, &tmap, &super)) {
+      const int box_cols = sq_tma_box_cols(wg2.WS, wg2.W);
+      if (box_cols <= 256 &&
+          make_square_tensor_map(in, d->ny, d->nx, d->n_planes, d->n_members, d->plane_stride, d->member_stride,
+                                 box_cols, &tmap, &super)) {
         tg.super_rows = super;
-        tg.box_cols = wg2.WS + 4;
-        tg.stage_floats = sq_tma_stage_floats(wg2.WS, d->n_members);
-        const size_t fixed = sq_tma_smem_bytes(wg2.WS, p.nb, d->n_members, 0);
-        const size_t budget = (size_t)env_int("NBH_SQ_TMA_SMEM", 26 * 1024);
-        int stages = (int)((budget > fixed ? budget - fixed : 0) / ((size_t)tg.stage_floats * 4));
-        stages = env_int("NBH_SQ_TMA_STAGES", stages);
-        if (stages >= 2) {
-          tg.n_stages = min(stages, 8);
+        tg.box_cols = box_cols;
+        tg.stage_floats = sq_tma_stage_floats(box_cols, d->n_members);
+        const int stages = env_int("NBH_SQ_TMA_STAGES", 3);
+        const size_t smem = sq_tma_smem_bytes(wg2.WS, wg2.W, p.nb, d->n_members, stages);
+        if (stages >= 2 && stages <= 8 && smem <= 200 * 1024) {
+          tg.n_stages = stages;
           wg = wg2;
+          wg.n_strips = n_bstrips;
+          // re-plan the y segmentation for block tasks (3 blocks per SM)
+          const long long units = d->n_planes * (long long)max(d->n_thresholds, 1) * n_bstrips;
+          int ysegs = env_int("NBH_SQW_YSEGS", 0);
+          if (ysegs <= 0) {
+            const double slots = (double)sm_count() * 3;
+            const int max_segs = max(1, d->ny / max(32, 6 * d->cells));
+            ysegs = (int)min((double)max_segs, max(1.0, ceil(5.0 * slots / (double)units)));
+          }
+          ysegs = max(1, min(ysegs, d->ny));
+          wg.seg_rows = (d->ny + ysegs - 1) / ysegs;
+          wg.n_ysegs = (d->ny + wg.seg_rows - 1) / wg.seg_rows;
+          wg.n_tasks = units * wg.n_ysegs;
           use_tma = true;
         }
       }
@@ -477,7 +493,7 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   if (use_tma) {
     NBH_CHECK_CUDA(cudaMemcpyAsync(w.tmap, &tmap, sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
     ProfileScope prof(st);
-    rc = launch_square_tma(p, wg, tg, w.tmap, tm, d->mask2d != nullptr, st);
+    rc = launch_square_tma(p, wg, tg, w.tmap, tm_warp, d->mask2d != nullptr, st);
   } else if (use_warp) {
     ProfileScope prof(st);
     const bool m2d = d->mask2d != nullptr;

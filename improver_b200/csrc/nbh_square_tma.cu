@@ -48,37 +48,34 @@ bool make_square_tensor_map(const float* in, int ny, int nx, long long n_planes,
   return true;
 }
 
-template <int G, int TM, bool M2D>
+template <int TM, bool M2D>
 static int launch_tma_one(const SqParams& p, const SqWarpGeom& g, const SqTmaGeom& tg, const CUtensorMap* map,
                           cudaStream_t st) {
-  auto kern = square_tma_kernel<G, TM, M2D>;
-  const size_t smem = sq_tma_smem_bytes(g.WS, p.nb, p.n_members, tg.n_stages);
+  auto kern = square_tma_kernel<TM, M2D>;
+  const size_t smem = sq_tma_smem_bytes(g.WS, g.W, p.nb, p.n_members, tg.n_stages);
   NBH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NBH_REQUIRE(g.n_tasks < (1LL << 31), "too many blocks (%lld); split the launch", g.n_tasks);
-  kern<<<(unsigned)g.n_tasks, 32, smem, st>>>(p, g, tg, map);
+  kern<<<(unsigned)g.n_tasks, kTmaWarps * 32, smem, st>>>(p, g, tg, map);
   NBH_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-template <int G>
-static int launch_tma_g(const SqParams& p, const SqWarpGeom& g, const SqTmaGeom& tg, const CUtensorMap* map, int tm,
-                        bool m2d, cudaStream_t st) {
-  switch ((tm << 1) | (m2d ? 1 : 0)) {
-    case 0: return launch_tma_one<G, 0, false>(p, g, tg, map, st);
-    case 1: return launch_tma_one<G, 0, true>(p, g, tg, map, st);
-    case 2: return launch_tma_one<G, 1, false>(p, g, tg, map, st);
-    case 3: return launch_tma_one<G, 1, true>(p, g, tg, map, st);
-    case 4: return launch_tma_one<G, 2, false>(p, g, tg, map, st);
-    default: return launch_tma_one<G, 2, true>(p, g, tg, map, st);
-  }
-}
-
 int launch_square_tma(const SqParams& p, const SqWarpGeom& g, const SqTmaGeom& tg, const CUtensorMap* map, int tm,
                       bool m2d, cudaStream_t st) {
-  if (g.WS == 64) return launch_tma_g<1>(p, g, tg, map, tm, m2d, st);
-  if (g.WS == 128) return launch_tma_g<2>(p, g, tg, map, tm, m2d, st);
-  set_error("unsupported TMA strip width %d", g.WS);
-  return 1;
+  NBH_REQUIRE(g.WS == 64, "unsupported TMA window width %d", g.WS);
+  switch ((tm << 1) | (m2d ? 1 : 0)) {
+    case 0: return launch_tma_one<0, false>(p, g, tg, map, st);
+    case 1: return launch_tma_one<0, true>(p, g, tg, map, st);
+    case 2: return launch_tma_one<1, false>(p, g, tg, map, st);
+    case 3: return launch_tma_one<1, true>(p, g, tg, map, st);
+    case 4: return launch_tma_one<2, false>(p, g, tg, map, st);
+    case 5: return launch_tma_one<2, true>(p, g, tg, map, st);
+    case 8: return launch_tma_one<4, false>(p, g, tg, map, st);
+    case 9: return launch_tma_one<4, true>(p, g, tg, map, st);
+    case 10: return launch_tma_one<5, false>(p, g, tg, map, st);
+    case 11: return launch_tma_one<5, true>(p, g, tg, map, st);
+    default: set_error("unsupported TMA kernel variant"); return 1;
+  }
 }
 
 }  // namespace nbh

@@ -60,34 +60,47 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map
       : "memory");
 }
 
-template <int G, int TM, bool M2D>
-__global__ void __launch_bounds__(32, 8)
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+constexpr int kTmaWarps = 4;     // warps per block sharing one TMA tile (x halo shared through smem)
+
+// Block = kTmaWarps warps working on adjacent 32*2-column windows of ONE shared
+// TMA tile per input row (all members).  The windows overlap by the halo inside
+// shared memory, so the x halo costs no extra global/L2 traffic.  Pipeline:
+// full[s] (TMA transaction barrier) / empty[s] (one arrival per warp); warp 0
+// lane 0 is the producer.  Each warp keeps its own ring, vertical sums and
+// horizontal scan exactly as in square_warp_kernel.
+template <int TM, bool M2D>
+__global__ void __launch_bounds__(kTmaWarps * 32, 3)
 square_tma_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g, const SqTmaGeom tg,
                   const CUtensorMap* __restrict__ tmap) {   // descriptor lives in global memory (workspace):
                                                             // a __grid_constant__ descriptor faults on this stack
   constexpr int VEC = 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int WS = g.WS, nb = p.nb, r = p.r, R = p.n_members, S = tg.n_stages;
 
-  // layout: stages (128-byte aligned) | mbarriers | hrow | rtab | ring
+  // layout: stages (128-byte aligned) | full[8] empty[8] | rtab | per warp: hrow, ring
   float* stages = reinterpret_cast<float*>(smem_raw);
   const size_t stage_bytes = (size_t)tg.stage_floats * 4;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)S * stage_bytes);
-  double* hrow = reinterpret_cast<double*>(bars + 8);
-  double* rtab = hrow + (WS + 2);
-  float* ring = reinterpret_cast<float*>(rtab + ((nb + 2) & ~1));
+  double* rtab = reinterpret_cast<double*>(bars + 16);
+  unsigned char* wbase = reinterpret_cast<unsigned char*>(rtab + ((nb + 2) & ~1)) +
+                         (size_t)warp * ((size_t)(WS + 2) * 8 + (size_t)nb * WS * 4);
+  double* hrow = reinterpret_cast<double*>(wbase);
+  float* ring = reinterpret_cast<float*>(wbase + (size_t)(WS + 2) * 8);
 
-  for (int k = lane + 1; k <= nb; k += 32) rtab[k] = 1.0 / (double)k;
+  for (int k = threadIdx.x + 1; k <= nb; k += blockDim.x) rtab[k] = 1.0 / (double)k;
 
   long long task = blockIdx.x;
-  const int strip = (int)(task % g.n_strips); task /= g.n_strips;
+  const int bstrip = (int)(task % g.n_strips); task /= g.n_strips;     // block strips
   const int yseg = (int)(task % g.n_ysegs); task /= g.n_ysegs;
   const int t = (int)(task % p.n_thr); task /= p.n_thr;
   const long long plane = task;
   const ThrDev thr = p.thr.t[TM ? t : 0];
 
-  const bool wrap = false;                       // (periodic x is served by the LDG kernels)
   const bool sum_only = (p.flags & NBH_SUM_ONLY) != 0;
   const int ya = yseg * g.seg_rows;
   const int yb = min(p.ny, ya + g.seg_rows);
@@ -95,199 +108,169 @@ square_tma_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g, const 
   const int n_rows = (yb - ya) + 2 * r;
   const int y_first = dir > 0 ? ya - r : yb - 1 + r;
 
-  int x0, load0, wk;
-  if (strip == 0) { x0 = 0; load0 = 0; wk = g.W0; }
-  else { x0 = g.W0 + (strip - 1) * g.W; load0 = x0 - g.hl; wk = g.W; }
-  const int c_out0 = x0 - load0;
+  // tile = kTmaWarps windows of WS columns at a pitch of W output columns
+  const int Wb = kTmaWarps * g.W;
+  const int tile0 = bstrip == 0 ? 0 : (Wb + g.hl) + (bstrip - 1) * Wb - g.hl;   // first tile column (global)
+  const int load0 = tile0 + warp * g.W;                                         // this warp's window
+  const bool first_window = (bstrip == 0 && warp == 0);
+  const int c_out0 = first_window ? 0 : g.hl;
+  const int wk = first_window ? g.W0 : g.W;
 
-  int c0[G], gxr[G];
-  bool col_active[G], colband[G];
-  bool any_band = false;
-#pragma unroll
-  for (int g2 = 0; g2 < G; ++g2) {
-    c0[g2] = g2 * 32 * VEC + lane * VEC;
-    gxr[g2] = load0 + c0[g2];
-    col_active[g2] = (gxr[g2] >= 0) && (gxr[g2] < p.nx);
-    colband[g2] = !sum_only && col_active[g2] &&
-                  ((gxr[g2] + VEC - 1 <= r) || (gxr[g2] >= p.nx - 1 - r && gxr[g2] + VEC - 1 < p.nx));
-    any_band = any_band || colband[g2];
-  }
+  const int c0 = lane * VEC;
+  const int gxr = load0 + c0;
+  const bool col_active = (gxr >= 0) && (gxr < p.nx);
+  const bool colband = !sum_only && col_active &&
+                       ((gxr + VEC - 1 <= r) || (gxr >= p.nx - 1 - r && gxr + VEC - 1 < p.nx));
   for (int s = 0; s < nb; ++s) {
 #pragma unroll
-    for (int g2 = 0; g2 < G; ++g2)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) ring[s * WS + c0[g2] + v] = 0.f;
+    for (int v = 0; v < VEC; ++v) ring[s * WS + c0 + v] = 0.f;
   }
   if (lane == 0) hrow[0] = 0.0;
 
   // ---- TMA pipeline set-up ----
-  const unsigned bar0 = smem_u32(bars);
+  const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + 8);
   const unsigned stage0 = smem_u32(stages);
   auto row_of = [&](int k) { return min(max(y_first + dir * k, 0), p.ny - 1); };   // clamped: always valid
   const unsigned box_bytes = (unsigned)(R * tg.box_cols * 4);
   auto box_start = [&](int y) {            // first column of the box of grid row y within its tensor row
-    return (load0 + (tg.super_rows ? (y & 1) * p.nx : 0)) & ~3;
+    return (tile0 + (tg.super_rows ? (y & 1) * p.nx : 0)) & ~3;
   };
-  auto issue_row = [&](int k) {            // lane 0 only
+  auto issue_row = [&](int k) {            // warp 0, lane 0 only
     const int s = k % S;
     const int y = row_of(k);
     const int cy = tg.super_rows ? (y >> 1) : y;
-    mbar_expect_tx(bar0 + 8 * s, box_bytes);
-    tma_load_4d(stage0 + (unsigned)(s * stage_bytes), tmap, box_start(y), cy, (int)plane, 0, bar0 + 8 * s);
+    mbar_expect_tx(full0 + 8 * s, box_bytes);
+    tma_load_4d(stage0 + (unsigned)(s * stage_bytes), tmap, box_start(y), cy, (int)plane, 0, full0 + 8 * s);
   };
-  if (lane == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(bar0 + 8 * s, 1);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, kTmaWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int k = 0; k < S && k < n_rows; ++k) issue_row(k);
   }
-  __syncwarp();
+  __syncthreads();
 
-  double V[G][VEC];
-  float P[G][VEC];
+  double V[VEC];
+  float P[VEC];
 #pragma unroll
-  for (int g2 = 0; g2 < G; ++g2)
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) { V[g2][v] = 0.0; P[g2][v] = 0.f; }
+  for (int v = 0; v < VEC; ++v) { V[v] = 0.0; P[v] = 0.f; }
   unsigned long long ne_left = 0, ne_right = 0, ne_top = 0, ne_bot = 0;
   float nanacc = 0.f;
   int slot = 0;
-  const bool strip_band = __any_sync(0xffffffffu, any_band);
+  const bool strip_band = __any_sync(0xffffffffu, colband);
   const long long obase0 = (plane * p.n_thr + t) * (long long)p.ny * p.nx;
+  const int BW = tg.box_cols;
 
-  unsigned m2_next[G];
-#pragma unroll
-  for (int g2 = 0; g2 < G; ++g2) {
-    m2_next[g2] = 0x0101u;
-    if (M2D && col_active[g2]) m2_next[g2] = ldm_packed<VEC>(p.mask2d + (long long)row_of(0) * p.nx + gxr[g2]);
-  }
+  unsigned m2_next = 0x0101u;
+  if (M2D && col_active) m2_next = ldm_packed<VEC>(p.mask2d + (long long)row_of(0) * p.nx + gxr);
 
   for (int k = 0; k < n_rows; ++k) {
     const int s = k % S;
+    // producer: refill the stage consumed in the previous iteration once every warp released it
+    if (threadIdx.x == 0 && k >= 1 && k - 1 + S < n_rows) {
+      const int sp = (k - 1) % S;
+      mbar_wait(empty0 + 8 * sp, (unsigned)(((k - 1) / S) & 1));
+      issue_row(k - 1 + S);
+    }
     const int yy = y_first + dir * k;
     const bool in_dom = (yy >= 0) && (yy < p.ny);
-    unsigned m2_cur[G];
-#pragma unroll
-    for (int g2 = 0; g2 < G; ++g2) {
-      m2_cur[g2] = m2_next[g2];
-      if (M2D && col_active[g2] && k + 1 < n_rows)
-        m2_next[g2] = ldm_packed<VEC>(p.mask2d + (long long)row_of(k + 1) * p.nx + gxr[g2]);
-    }
-    mbar_wait(bar0 + 8 * s, (unsigned)((k / S) & 1));
+    const unsigned m2_cur = m2_next;
+    if (M2D && col_active && k + 1 < n_rows)
+      m2_next = ldm_packed<VEC>(p.mask2d + (long long)row_of(k + 1) * p.nx + gxr);
+    mbar_wait(full0 + 8 * s, (unsigned)((k / S) & 1));
     const int yrow = row_of(k);
-    const int delta = load0 + (tg.super_rows ? (yrow & 1) * p.nx : 0) - box_start(yrow);   // 0 or 2
-    const float* st = stages + (size_t)s * tg.stage_floats + delta;
-    const int BW = tg.box_cols;
+    const int delta = tile0 + (tg.super_rows ? (yrow & 1) * p.nx : 0) - box_start(yrow);   // 0 or 2
+    const float* col = stages + (size_t)s * tg.stage_floats + delta + warp * g.W + c0;
     const bool flagged = in_dom && !sum_only && (strip_band || yy <= r || yy >= p.ny - 1 - r);
+    float acc0 = 0.f, acc1 = 0.f;
     if (!flagged) {
-#pragma unroll
-      for (int g2 = 0; g2 < G; ++g2) {
-        float acc0 = 0.f, acc1 = 0.f;
-        const float* col = st + c0[g2];
 #pragma unroll 6
-        for (int m = 0; m < R; ++m) {
-          const float2 d = *reinterpret_cast<const float2*>(col + (size_t)m * BW);
-          nanacc = max_nan(nanacc, fabsf(d.x));
-          nanacc = max_nan(nanacc, fabsf(d.y));
-          float t0 = truth_value_sum<TM>(d.x, thr), t1 = truth_value_sum<TM>(d.y, thr);
-          if (M2D) {
-            t0 = (m2_cur[g2] & 0xffu) ? t0 : 0.f;
-            t1 = (m2_cur[g2] & 0xff00u) ? t1 : 0.f;
-          }
-          acc0 += t0; acc1 += t1;
+      for (int m = 0; m < R; ++m) {
+        const float2 d = *reinterpret_cast<const float2*>(col + (size_t)m * BW);
+        nanacc = max_nan(nanacc, fabsf(d.x));
+        nanacc = max_nan(nanacc, fabsf(d.y));
+        float t0 = truth_value_sum<TM>(d.x, thr), t1 = truth_value_sum<TM>(d.y, thr);
+        if (M2D) {
+          t0 = (m2_cur & 0xffu) ? t0 : 0.f;
+          t1 = (m2_cur & 0xff00u) ? t1 : 0.f;
         }
-        P[g2][0] = acc0; P[g2][1] = acc1;
+        acc0 += t0; acc1 += t1;
       }
     } else {
-#pragma unroll
-      for (int g2 = 0; g2 < G; ++g2) {
-        float acc0 = 0.f, acc1 = 0.f;
-        unsigned long long ne = 0;
-        const float* col = st + c0[g2];
-        const bool v0 = !M2D || (m2_cur[g2] & 0xffu), v1 = !M2D || (m2_cur[g2] & 0xff00u);
+      unsigned long long ne = 0;
+      const bool v0 = !M2D || (m2_cur & 0xffu), v1 = !M2D || (m2_cur & 0xff00u);
 #pragma unroll 2
-        for (int m = 0; m < R; ++m) {
-          const float2 d = *reinterpret_cast<const float2*>(col + (size_t)m * BW);
-          nanacc = max_nan(nanacc, fabsf(d.x));
-          nanacc = max_nan(nanacc, fabsf(d.y));
-          float t0 = truth_value_sum<TM>(d.x, thr), t1 = truth_value_sum<TM>(d.y, thr);
-          t0 = v0 ? t0 : 0.f;
-          t1 = v1 ? t1 : 0.f;
-          acc0 += t0; acc1 += t1;
-          if (!v0 || !v1 || truth_not_one(d.x, thr) || truth_not_one(d.y, thr)) ne |= 1ull << m;
-        }
-        P[g2][0] = acc0; P[g2][1] = acc1;
-        if (col_active[g2]) {
-          if (colband[g2] && (gxr[g2] + VEC - 1 <= r)) ne_left |= ne;
-          if (colband[g2] && (gxr[g2] >= p.nx - 1 - r)) ne_right |= ne;
-          if (yy <= r) ne_top |= ne;
-          if (yy >= p.ny - 1 - r) ne_bot |= ne;
-        }
+      for (int m = 0; m < R; ++m) {
+        const float2 d = *reinterpret_cast<const float2*>(col + (size_t)m * BW);
+        nanacc = max_nan(nanacc, fabsf(d.x));
+        nanacc = max_nan(nanacc, fabsf(d.y));
+        float t0 = truth_value_sum<TM>(d.x, thr), t1 = truth_value_sum<TM>(d.y, thr);
+        t0 = v0 ? t0 : 0.f;
+        t1 = v1 ? t1 : 0.f;
+        acc0 += t0; acc1 += t1;
+        if (!v0 || !v1 || truth_not_one(d.x, thr) || truth_not_one(d.y, thr)) ne |= 1ull << m;
+      }
+      if (col_active) {
+        if (colband && (gxr + VEC - 1 <= r)) ne_left |= ne;
+        if (colband && (gxr >= p.nx - 1 - r)) ne_right |= ne;
+        if (yy <= r) ne_top |= ne;
+        if (yy >= p.ny - 1 - r) ne_bot |= ne;
       }
     }
-    __syncwarp();                                   // every lane has read stage s
-    if (lane == 0 && k + S < n_rows) issue_row(k + S);
+    P[0] = acc0; P[1] = acc1;
+    __syncwarp();                                   // every lane of this warp has read stage s
+    if (lane == 0) mbar_arrive(empty0 + 8 * s);
 
-    // ---- vertical sums through the ring ----
+    // ---- vertical sums through the warp-private ring ----
 #pragma unroll
-    for (int g2 = 0; g2 < G; ++g2)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        if (!in_dom || !col_active[g2]) P[g2][v] = 0.f;
-        const int ri = slot * WS + c0[g2] + v;
-        const float old = ring[ri];
-        ring[ri] = P[g2][v];
-        V[g2][v] += (double)P[g2][v] - (double)old;
-      }
+    for (int v = 0; v < VEC; ++v) {
+      if (!in_dom || !col_active) P[v] = 0.f;
+      const int ri = slot * WS + c0 + v;
+      const float old = ring[ri];
+      ring[ri] = P[v];
+      V[v] += (double)P[v] - (double)old;
+    }
     slot = (slot + 1 == nb) ? 0 : slot + 1;
     if (k < 2 * r) continue;
 
     // ---- horizontal window: float64 warp scan + prefix difference ----
-    double carry = 0.0;
+    const double s1 = V[0] + V[1];
+    double incl = s1;
 #pragma unroll
-    for (int g2 = 0; g2 < G; ++g2) {
-      const double s1 = V[g2][0] + V[g2][1];
-      double incl = s1;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const double o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
-      }
-      const double excl = carry + incl - s1;
-      hrow[c0[g2] + 1] = excl + V[g2][0];
-      hrow[c0[g2] + 2] = excl + s1;
-      if (g2 + 1 < G) carry += __shfl_sync(0xffffffffu, incl, 31);
+    for (int d = 1; d < 32; d <<= 1) {
+      const double o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
     }
+    const double excl = incl - s1;
+    hrow[c0 + 1] = excl + V[0];
+    hrow[c0 + 2] = excl + s1;
     __syncwarp();
     const int yo = y_first + dir * (k - r);
-    const int rows_in = min(yo + r, p.ny - 1) - max(yo - r, 0) + 1;
-    const double rrow = rtab[rows_in] * p.inv_members;
+    const bool is_out = (c0 >= c_out0) && (c0 < c_out0 + wk) && col_active;
+    if (is_out) {
+      const int rows_in = min(yo + r, p.ny - 1) - max(yo - r, 0) + 1;
+      const double rrow = rtab[rows_in] * p.inv_members;
+      const long long pt0 = (long long)yo * p.nx + gxr;
+      float o[VEC];
 #pragma unroll
-    for (int g2 = 0; g2 < G; ++g2) {
-      const bool is_out = (c0[g2] >= c_out0) && (c0[g2] < c_out0 + wk) && col_active[g2];
-      if (is_out) {
-        const long long pt0 = (long long)yo * p.nx + gxr[g2];
-        float o[VEC];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          const int cc = c0[g2] + v;
-          const double Sw = hrow[cc + r + 1] - hrow[max(cc - r, 0)];
-          if (sum_only) {
-            o[v] = (float)Sw;
-          } else if (M2D) {
-            o[v] = (float)(Sw * p.rcp_count[pt0 + v] * p.inv_members);
-          } else {
-            const int xo = gxr[g2] + v;
-            const int cols_in = wrap ? nb : (min(xo + r, p.nx - 1) - max(xo - r, 0) + 1);
-            o[v] = (float)(Sw * rrow * rtab[cols_in]);
-          }
+      for (int v = 0; v < VEC; ++v) {
+        const int cc = c0 + v;
+        const double Sw = hrow[cc + r + 1] - hrow[max(cc - r, 0)];
+        if (sum_only) {
+          o[v] = (float)Sw;
+        } else if (M2D) {
+          o[v] = (float)(Sw * p.rcp_count[pt0 + v] * p.inv_members);
+        } else {
+          const int xo = gxr + v;
+          const int cols_in = min(xo + r, p.nx - 1) - max(xo - r, 0) + 1;
+          o[v] = (float)(Sw * rrow * rtab[cols_in]);
         }
-        VecLoad<VEC>::st(p.out + obase0 + pt0, o);
-        if (p.out_mask) {
+      }
+      VecLoad<VEC>::st(p.out + obase0 + pt0, o);
+      if (p.out_mask) {
 #pragma unroll
-          for (int v = 0; v < VEC; ++v)
-            p.out_mask[obase0 + pt0 + v] = (M2D && p.mask2d[pt0 + v] == 0) ? 1 : 0;
-        }
+        for (int v = 0; v < VEC; ++v)
+          p.out_mask[obase0 + pt0 + v] = (M2D && p.mask2d[pt0 + v] == 0) ? 1 : 0;
       }
     }
     __syncwarp();                                   // hrow is rewritten by the next row
@@ -315,14 +298,15 @@ square_tma_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g, const 
   }
 }
 
-inline int sq_tma_stage_floats(int WS, int n_members) { return (n_members * (WS + 4) + 31) / 32 * 32; }
+// tile columns: kTmaWarps windows at pitch W + the last window's remainder, + 4 for the aligned box start
+inline int sq_tma_box_cols(int WS, int W) { return ((kTmaWarps - 1) * W + WS + 4 + 3) / 4 * 4; }
+inline int sq_tma_stage_floats(int box_cols, int n_members) { return (n_members * box_cols + 31) / 32 * 32; }
 
-inline size_t sq_tma_smem_bytes(int WS, int nb, int n_members, int n_stages) {
-  // Rounded up to a multiple of 1 KB: co-resident blocks are packed at the
-  // requested size, and a TMA destination must be 128-byte aligned (an odd
-  // size makes the second block on an SM fault with "illegal instruction").
-  const size_t raw = (size_t)n_stages * sq_tma_stage_floats(WS, n_members) * 4 + 64 + (size_t)(WS + 2) * 8 +
-                     (size_t)((nb + 2) & ~1) * 8 + (size_t)nb * WS * 4;
+inline size_t sq_tma_smem_bytes(int WS, int W, int nb, int n_members, int n_stages) {
+  // Rounded up to a multiple of 1 KB (TMA destinations must be 128-byte aligned).
+  const size_t raw = (size_t)n_stages * sq_tma_stage_floats(sq_tma_box_cols(WS, W), n_members) * 4 + 128 +
+                     (size_t)((nb + 2) & ~1) * 8 +
+                     (size_t)kTmaWarps * ((size_t)(WS + 2) * 8 + (size_t)nb * WS * 4);
   return (raw + 1023) / 1024 * 1024;
 }
 

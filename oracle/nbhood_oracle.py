@@ -34,6 +34,7 @@ COMPARATORS = {
     ">=": (operator.ge, "greater_than_or_equal_to"), "ge": (operator.ge, "greater_than_or_equal_to"),
     "<": (operator.lt, "less_than"), "lt": (operator.lt, "less_than"),
     "<=": (operator.le, "less_than_or_equal_to"), "le": (operator.le, "less_than_or_equal_to"),
+    "==": (operator.eq, "equal_to"), "eq": (operator.eq, "equal_to"),
 }
 
 
@@ -258,6 +259,26 @@ def land_sea_neighbourhood(data, land_mask, **kw):
     lv, lm = neighbourhood_cube(data, land, **kw)
     sv, sm = neighbourhood_cube(data, sea, **kw)
     return np.where(lm, 0, lv) + np.where(sm, 0, sv)
+
+
+def neighbourhood_with_zone_masks(data, masks, weights=None, **kw):
+    """improver/nbhood/use_nbhood.py:194-262: every 2-D slice is neighbourhooded
+    once per zone mask (re_mask=False); with `weights` (zone, y, x) the zone axis
+    is collapsed by a NaN-aware weighted mean (np.ma.average renormalises)."""
+    lead = data.shape[:-2]
+    flat = data.reshape((-1,) + data.shape[-2:])
+    out = np.empty((flat.shape[0], masks.shape[0]) + data.shape[-2:], dtype=F32)
+    kw = dict(kw, re_mask=False)
+    for i in range(flat.shape[0]):
+        for z in range(masks.shape[0]):
+            out[i, z] = neighbourhood(flat[i], masks[z], **kw)
+    if weights is not None:
+        collapsed = np.ma.average(np.ma.masked_invalid(out), axis=1,
+                                  weights=np.broadcast_to(weights, out.shape))
+        res = np.ma.getdata(collapsed).astype(F32)
+        res[np.ma.getmaskarray(collapsed)] = np.nan
+        return res.reshape(lead + data.shape[-2:])
+    return out.reshape(lead + out.shape[1:])
 
 
 # --------------------------------------------------------------------------- #

@@ -278,3 +278,36 @@ def test_boxsum_matches_oracle():
     np.testing.assert_array_equal(boxsum(ints, 3, mode="constant"), orc.boxsum(ints, 3, mode="constant"))
     cum = data.cumsum(-2).cumsum(-1)
     np.testing.assert_allclose(boxsum(cum, 3, cumsum=False), orc.boxsum(cum, 3, cumsum=False))
+
+
+def test_apply_neighbourhood_with_zone_masks_vs_oracle():
+    """improver/nbhood/use_nbhood.py:194-262."""
+    from improver_b200.cube import Coord, Cube
+    from improver_b200.nbhood.use_nbhood import ApplyNeighbourhoodProcessingWithAMask
+
+    rng = np.random.default_rng(8)
+    data = rng.random((2, 30, 36)).astype(np.float32)
+    zones = rng.integers(0, 3, (30, 36))
+    zones[:8, :8] = 3                                         # "sea": in no zone at all
+    masks = np.stack([(zones == z).astype(np.int8) for z in range(3)])
+    weights = rng.random((3, 30, 36)).astype(np.float32)
+    weights /= weights.sum(axis=0, keepdims=True)
+    cube = set_up_probability_cube(data, [1.0, 2.0])
+    y, x = cube.coord(axis="y"), cube.coord(axis="x")
+    zcoord = Coord(np.arange(3, dtype=np.float32), "topographic_zone", "m")
+    mask_cube = Cube(masks, "topography_mask", "1", [(zcoord, 0), (y.copy(), 1), (x.copy(), 2)])
+    plugin = ApplyNeighbourhoodProcessingWithAMask("topographic_zone", "square", 4000)
+    result = plugin(cube, mask_cube)
+    exp = orc.neighbourhood_with_zone_masks(data, masks, method="square", cells=2)
+    assert result.shape == (2, 3, 30, 36)
+    got = np.asarray(result.data)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(exp))
+    np.testing.assert_allclose(got[~np.isnan(exp)], exp[~np.isnan(exp)], atol=1e-5)
+    wcube = Cube(weights, "topographic_zone_weights", "1", [(zcoord.copy(), 0), (y.copy(), 1), (x.copy(), 2)])
+    collapsed = ApplyNeighbourhoodProcessingWithAMask("topographic_zone", "square", 4000,
+                                                      collapse_weights=wcube)(cube, mask_cube)
+    exp_c = orc.neighbourhood_with_zone_masks(data, masks, weights=weights, method="square", cells=2)
+    assert collapsed.shape == (2, 30, 36)
+    gotc = np.asarray(collapsed.data)
+    np.testing.assert_array_equal(np.isnan(gotc), np.isnan(exp_c))
+    np.testing.assert_allclose(gotc[~np.isnan(exp_c)], exp_c[~np.isnan(exp_c)], atol=1e-5)
