@@ -170,29 +170,38 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
     }
   };
   // horizontal part 2: window sum = prefix difference, normalise, store
+  // lane-constant pieces of the output stage, hoisted out of the row loop
+  bool is_out[G];
+  int idx_hi[G][VEC], idx_lo[G][VEC];
+  double rcol[G][VEC];                                  // 1 / (window columns inside the domain) / members
+#pragma unroll
+  for (int g2 = 0; g2 < G; ++g2) {
+    is_out[g2] = (c0[g2] >= c_out0) && (c0[g2] < c_out0 + wk) && (gxr[g2] < p.nx) && col_active[g2];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int cc = c0[g2] + v;
+      idx_hi[g2][v] = cc + r + 1;
+      idx_lo[g2][v] = max(cc - r, 0);
+      const int xo = gx[g2] + v;
+      const int cols_in = wrap ? nb : (min(xo + r, p.nx - 1) - max(xo - r, 0) + 1);
+      rcol[g2][v] = sum_only ? 1.0 : rtab[min(max(cols_in, 1), nb)] * p.inv_members;
+    }
+  }
   auto h_store = [&](int k, const double* hr) {
     const int yo = y_first + dir * (k - r);              // centre row of the window
     const int rows_in = min(yo + r, p.ny - 1) - max(yo - r, 0) + 1;
-    const double rrow = rtab[rows_in] * p.inv_members;
+    const double rrow = sum_only ? 1.0 : rtab[rows_in];
+    const long long row_off = (long long)yo * p.nx;
 #pragma unroll
     for (int g2 = 0; g2 < G; ++g2) {
-      const bool is_out = (c0[g2] >= c_out0) && (c0[g2] < c_out0 + wk) && (gxr[g2] < p.nx) && col_active[g2];
-      if (is_out) {
-        const long long pt0 = (long long)yo * p.nx + gx[g2];
+      if (is_out[g2]) {
+        const long long pt0 = row_off + gx[g2];
         float o[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-          const int cc = c0[g2] + v;
-          const double S = hr[cc + r + 1] - hr[max(cc - r, 0)];
-          if (sum_only) {
-            o[v] = (float)S;
-          } else if (M2D) {
-            o[v] = (float)(S * p.rcp_count[pt0 + v] * p.inv_members);
-          } else {
-            const int xo = gx[g2] + v;
-            const int cols_in = wrap ? nb : (min(xo + r, p.nx - 1) - max(xo - r, 0) + 1);
-            o[v] = (float)(S * rrow * rtab[cols_in]);
-          }
+          const double S = hr[idx_hi[g2][v]] - hr[idx_lo[g2][v]];
+          if (M2D && !sum_only) o[v] = (float)(S * p.rcp_count[pt0 + v] * p.inv_members);
+          else o[v] = (float)(S * rrow * rcol[g2][v]);
         }
         VecLoad<VEC>::st(p.out + obase0 + pt0, o);
         if (p.out_mask) {

@@ -311,3 +311,18 @@ def test_apply_neighbourhood_with_zone_masks_vs_oracle():
     gotc = np.asarray(collapsed.data)
     np.testing.assert_array_equal(np.isnan(gotc), np.isnan(exp_c))
     np.testing.assert_allclose(gotc[~np.isnan(exp_c)], exp_c[~np.isnan(exp_c)], atol=1e-5)
+
+
+def test_nbhood_land_and_sea_vs_oracle():
+    """improver/cli/nbhood_land_and_sea.py:131-184 (config 2 semantics)."""
+    from improver_b200.nbhood.land_and_sea import nbhood_land_and_sea
+
+    rng = np.random.default_rng(12)
+    data = rng.random((2, 44, 51)).astype(np.float32)
+    land = (rng.random((44, 51)) < 0.55).astype(np.int8)
+    cube = set_up_probability_cube(data, [1.0, 2.0])
+    mask_cube = set_up_variable_cube(land.astype(np.float32), name="land_binary_mask", units="1")
+    for shape, cells in (("square", 3), ("circular", 3)):
+        result = nbhood_land_and_sea(cube, mask_cube, neighbourhood_shape=shape, radii=6000)
+        exp = orc.land_sea_neighbourhood(data, land, method=shape, cells=cells)
+        np.testing.assert_allclose(np.asarray(result.data), exp, atol=1e-5)
