@@ -61,6 +61,57 @@ __global__ void pct_pad_kernel(const float* in, float* padv, int ny, int nx, int
   }
 }
 
+// U order statistics of the warp's keys at once (MSB-first bisection), then
+// the float32 linear interpolation of numpy's percentile.
+template <int KPL, int U>
+__device__ __forceinline__ void select_group(const unsigned (&key)[KPL], const PctParams& p, int q0, int lane,
+                                             long long obase) {
+  int kk[U];
+  unsigned prefix[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) { kk[u] = p.k_lo[q0 + u]; prefix[u] = 0; }
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    unsigned cand[U];
+    int cnt[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { cand[u] = prefix[u] | (1u << bit); cnt[u] = 0; }
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) cnt[u] += key[j] < cand[u];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      cnt[u] = __reduce_add_sync(0xffffffffu, cnt[u]);
+      if (cnt[u] <= kk[u]) prefix[u] = cand[u];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int q = q0 + u;
+    const int k = kk[u];
+    // (k+1)-th: same value if duplicated, else the smallest key above
+    int cle = 0;
+    unsigned nxt = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      cle += key[j] <= prefix[u];
+      if (key[j] > prefix[u]) nxt = min(nxt, key[j]);
+    }
+    cle = __reduce_add_sync(0xffffffffu, cle);
+    nxt = __reduce_min_sync(0xffffffffu, nxt);
+    const float lo = key2f(prefix[u]);
+    const float hi = (k + 1 >= p.N || cle >= k + 2) ? lo : key2f(nxt);
+    // numpy _lerp (float32): a + (b-a)*t, and b - (b-a)*(1-t) where t >= 0.5
+    const float t = p.gamma[q];
+    const float diff = __fsub_rn(hi, lo);
+    float res = __fadd_rn(lo, __fmul_rn(diff, t));
+    if (t >= 0.5f) res = __fsub_rn(hi, __fmul_rn(diff, __fsub_rn(1.0f, t)));
+    if (lane == 0) p.out[obase + (long long)q * p.ny * p.nx] = res;
+  }
+}
+
 template <int KPL>
 __global__ void __launch_bounds__(256)
 percentile_kernel(const PctParams p) {
@@ -116,38 +167,20 @@ percentile_kernel(const PctParams p) {
 #pragma unroll
     for (int j = 0; j < KPL; ++j) key[j] = my_off[j] >= 0 ? tile[base + my_off[j]] : 0xffffffffu;
 
-    for (int q = 0; q < p.n_pct; ++q) {
-      const int k = p.k_lo[q];
-      // k-th smallest key (0-based): MSB-first bisection
-      unsigned prefix = 0;
-#pragma unroll 1
-      for (int bit = 31; bit >= 0; --bit) {
-        const unsigned cand = prefix | (1u << bit);
-        int cnt = 0;
-#pragma unroll
-        for (int j = 0; j < KPL; ++j) cnt += key[j] < cand;
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (cnt <= k) prefix = cand;
+    // Percentiles are processed up to five at a time: their bisections are
+    // independent, so interleaving them hides the latency of the warp reductions.
+    const long long obase = (s * p.n_pct * (long long)p.ny + y) * p.nx + x;
+    int q0 = 0;
+    while (q0 < p.n_pct) {
+      const int nu = min(5, p.n_pct - q0);
+      switch (nu) {
+        case 5: select_group<KPL, 5>(key, p, q0, lane, obase); break;
+        case 4: select_group<KPL, 4>(key, p, q0, lane, obase); break;
+        case 3: select_group<KPL, 3>(key, p, q0, lane, obase); break;
+        case 2: select_group<KPL, 2>(key, p, q0, lane, obase); break;
+        default: select_group<KPL, 1>(key, p, q0, lane, obase); break;
       }
-      // (k+1)-th: same value if duplicated, else the smallest key above
-      int cle = 0;
-      unsigned nxt = 0xffffffffu;
-#pragma unroll
-      for (int j = 0; j < KPL; ++j) {
-        cle += key[j] <= prefix;
-        if (key[j] > prefix) nxt = min(nxt, key[j]);
-      }
-      cle = __reduce_add_sync(0xffffffffu, cle);
-      nxt = __reduce_min_sync(0xffffffffu, nxt);
-      const float lo = key2f(prefix);
-      const float hi = (k + 1 >= p.N || cle >= k + 2) ? lo : key2f(nxt);
-      // numpy _lerp (float32): a + (b-a)*t, and b - (b-a)*(1-t) where t >= 0.5
-      const float t = p.gamma[q];
-      const float diff = __fsub_rn(hi, lo);
-      float res = __fadd_rn(lo, __fmul_rn(diff, t));
-      if (t >= 0.5f) res = __fsub_rn(hi, __fmul_rn(diff, __fsub_rn(1.0f, t)));
-      if (lane == 0)
-        p.out[((s * p.n_pct + q) * p.ny + y) * (long long)p.nx + x] = res;
+      q0 += nu;
     }
   }
 }
