@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(_HERE, "lib", "libimprover_b200.so")
+LIBPATH = os.environ.get("IMPROVER_B200_LIB", os.path.join(_HERE, "lib", "libimprover_b200.so"))
 
 OPS = {">": 0, "gt": 0, "GT": 0, ">=": 1, "ge": 1, "GE": 1,
        "<": 2, "lt": 2, "LT": 2, "<=": 3, "le": 3, "LE": 3, "==": 4, "eq": 4, "EQ": 4}

@@ -172,8 +172,12 @@ template <> struct VecLoad<1> {
 };
 template <> struct VecLoad<2> {
   static __device__ __forceinline__ void ld(const float* p, float* v) {
+#if defined(NBH_LD_NOALLOC)
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "l"(p));
+#else
     float2 t = __ldg(reinterpret_cast<const float2*>(p));
     v[0] = t.x; v[1] = t.y;
+#endif
   }
   static __device__ __forceinline__ void st(float* p, const float* v) {
     *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);

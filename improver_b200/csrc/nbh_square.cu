@@ -327,6 +327,7 @@ static bool plan_square_warp(const NbhDesc& d, int vec, SqWarpGeom* g) {
   g->seg_rows = (d.ny + ysegs - 1) / ysegs;
   g->n_ysegs = (d.ny + g->seg_rows - 1) / g->seg_rows;
   g->n_tasks = units * g->n_ysegs;
+  g->n_sm = env_int("NBH_SQW_REMAP", 0) ? sm_count() : 0;
   return true;
 }
 

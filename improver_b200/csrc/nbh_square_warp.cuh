@@ -33,6 +33,8 @@ struct SqWarpGeom {
   int hl;        // left halo of strips > 0 (multiple of VEC, >= r)
   int n_strips, n_ysegs, seg_rows;
   long long n_tasks;
+  int n_sm;      // > 0: remap block -> task so that each SM works through a contiguous run of tasks
+                 // (adjacent strips share their halo columns through that SM's L1)
 };
 
 template <int VEC, int G, int TM, bool M2D, bool ROWS, bool FULL, int MB>
@@ -54,6 +56,11 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
   __syncthreads();     // the only block-level barrier in the kernel
 
   long long task = (long long)blockIdx.x * kSqWarpsPerBlock + warp;
+  if (g.n_sm > 0) {
+    const long long per = (g.n_tasks + g.n_sm - 1) / g.n_sm;
+    task = (long long)(blockIdx.x % g.n_sm) * per + blockIdx.x / g.n_sm;
+    if (blockIdx.x / g.n_sm >= per) return;
+  }
   if (task >= g.n_tasks) return;
   const int strip = (int)(task % g.n_strips); task /= g.n_strips;
   const int yseg = (int)(task % g.n_ysegs); task /= g.n_ysegs;
@@ -423,7 +430,8 @@ static int launch_square_warp_one(const SqParams& p, const SqWarpGeom& g, cudaSt
   auto kern = square_warp_kernel<VEC, G, TM, M2D, ROWS, FULL, MB>;
   const size_t smem = sq_warp_smem_bytes(VEC, G, p.nb);
   NBH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long blocks = (g.n_tasks + kSqWarpsPerBlock - 1) / kSqWarpsPerBlock;
+  long long blocks = (g.n_tasks + kSqWarpsPerBlock - 1) / kSqWarpsPerBlock;
+  if (g.n_sm > 0) blocks = (g.n_tasks + g.n_sm - 1) / g.n_sm * g.n_sm;
   NBH_REQUIRE(blocks < (1LL << 31), "too many blocks (%lld); split the launch", blocks);
   kern<<<(unsigned)blocks, kSqWarpsPerBlock * 32, smem, st>>>(p, g);
   NBH_CHECK_CUDA(cudaGetLastError());
