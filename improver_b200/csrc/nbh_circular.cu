@@ -15,6 +15,8 @@
 
 namespace nbh {
 
+int env_int(const char* name, int dflt);
+
 struct CircParams {
   const float* in;
   float* out;
@@ -322,6 +324,98 @@ __global__ void __launch_bounds__(256) circ_gather_kernel(const CircGlobalParams
   }
 }
 
+
+// Shared-memory tiled gather: a block stages the (TH + 2r) x (TW + 2r + 1)
+// window of prefix values its TH x TW outputs need (each value is then read
+// ~2(2r+1) times from shared memory instead of L2).
+constexpr int kCircTW = 64;
+
+__global__ void __launch_bounds__(256) circ_gather_tiled_kernel(const CircGlobalParams p, int TH, int tiles_x,
+                                                                int tiles_y) {
+  extern __shared__ __align__(16) unsigned char smem_c[];
+  const int r = p.r;
+  const int TC = kCircTW + 2 * r + 1, TR = TH + 2 * r;
+  double* tile = reinterpret_cast<double*>(smem_c);            // [TR][TC], col j <-> global col x0 - r - 1 + j
+  int* wtab_s = reinterpret_cast<int*>(tile + (size_t)TR * TC);
+  for (int k = threadIdx.x; k <= r; k += blockDim.x) wtab_s[k] = p.wtab[k];
+
+  long long bid = blockIdx.x;
+  const int tx = (int)(bid % tiles_x); bid /= tiles_x;
+  const int ty = (int)(bid % tiles_y); bid /= tiles_y;
+  const int b = (int)bid;
+  const int x0 = tx * kCircTW, y0 = ty * TH;
+  const long long per_plane = (long long)p.ny * p.nx;
+  const double* pre = p.prefix + (long long)b * per_plane;
+#pragma unroll 8
+  for (int i = threadIdx.x; i < TR * TC; i += blockDim.x) {
+    const int jr = i / TC, jc = i - jr * TC;
+    const int ys = min(max(y0 - r + jr, 0), p.ny - 1);          // edge replication in y
+    const int gc = x0 - r - 1 + jc;
+    tile[i] = gc < 0 ? 0.0 : pre[(long long)ys * p.nx + min(gc, p.nx - 1)];
+  }
+  __syncthreads();
+
+  const int lx = threadIdx.x % kCircTW;
+  const int x = x0 + lx;
+  if (x >= p.nx) return;
+  const long long plane = p.plane0 + b;
+  const int cshift = r + 1 - x0;                                // tile column of global column gc: gc + cshift
+  for (int ly = threadIdx.x / kCircTW; ly < TH; ly += blockDim.x / kCircTW) {
+    const int y = y0 + ly;
+    if (y >= p.ny) break;
+    double S = 0.0;
+    for (int dy = -r; dy <= r; ++dy) {
+      const int w = wtab_s[dy < 0 ? -dy : dy];
+      const double* row = tile + (size_t)(ly + r + dy) * TC + cshift;   // indexable by global column >= -1
+      const int lo = max(x - w, 0), hi = min(x + w, p.nx - 1);
+      double s = row[hi] - row[lo - 1];
+      const int nl = lo - (x - w), nr = (x + w) - hi;             // replicated edge cells (mode="nearest")
+      if (nl > 0) s += (double)nl * (row[0] - row[-1]);
+      if (nr > 0) s += (double)nr * (row[p.nx - 1] - row[p.nx - 2]);
+      S += s;
+    }
+    const long long pt = (long long)y * p.nx + x;
+    const long long o = (plane * p.n_thr + p.t) * per_plane + pt;
+    float res;
+    if (p.flags & NBH_SUM_ONLY) {
+      res = (float)S;
+    } else {
+      const float Af = p.mask2d ? p.area[pt] : p.area_const;
+      res = (Af == 0.f) ? __int_as_float(0x7fc00000) : (float)(S / (double)Af * p.inv_members);
+    }
+    p.out[o] = res;
+    if (p.out_mask) p.out_mask[o] = (p.mask2d && p.mask2d[pt] == 0) ? 1 : 0;
+  }
+}
+
+// pick the tallest tile that fits; 0 = use the direct (L2) gather
+static int circ_tile_rows(int r, int nx, size_t* smem) {
+  // measured on B200: the tile pays off while it is small enough for several blocks per SM
+  if (nx < 3 || r > env_int("NBH_CIRC_TILED_MAX_R", 16)) return 0;
+  for (int th : {64, 32, 16, 8}) {
+    const size_t bytes = (size_t)(th + 2 * r) * (kCircTW + 2 * r + 1) * 8 + (size_t)(r + 1) * 4 + 16;
+    if (bytes <= (th >= 32 ? 100u : 200u) * 1024) { *smem = bytes; return th; }
+  }
+  return 0;
+}
+
+static int launch_circ_gather(const CircGlobalParams& g, int ny, int nx, cudaStream_t st) {
+  size_t smem = 0;
+  const int th = (g.cprefix || env_int("NBH_CIRC_TILED", 1) == 0) ? 0 : circ_tile_rows(g.r, nx, &smem);
+  if (th > 0) {
+    NBH_CHECK_CUDA(cudaFuncSetAttribute(circ_gather_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    const int tiles_x = (nx + kCircTW - 1) / kCircTW, tiles_y = (ny + th - 1) / th;
+    const long long blocks = (long long)tiles_x * tiles_y * g.n_batch;
+    NBH_REQUIRE(blocks < (1LL << 31), "too many blocks");
+    circ_gather_tiled_kernel<<<(unsigned)blocks, 256, smem, st>>>(g, th, tiles_x, tiles_y);
+  } else {
+    const long long outs = (long long)g.n_batch * ny * nx;
+    circ_gather_kernel<<<(unsigned)((outs + 255) / 256), 256, (size_t)(g.r + 1) * 4, st>>>(g);
+  }
+  return 0;
+}
+
 // area_sum for an external mask at large radius, from the prefix of the mask itself
 __global__ void circ_mask_to_float_kernel(const uint8_t* mask, float* as_float, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -338,7 +432,7 @@ int env_int(const char* name, int dflt);
 static bool use_global_path(const NbhDesc& d) {
   if (d.cells > kCircSmemMaxRadius) return true;
   if (d.flags & NBH_WEIGHTED) return false;
-  return d.cells >= env_int("NBH_CIRC_GLOBAL_MIN_R", 7);   // measured crossover on B200 (profiles/)
+  return d.cells >= env_int("NBH_CIRC_GLOBAL_MIN_R", 1);   // measured on B200: wins at every radius
 }
 
 struct CircWorkspace {
@@ -436,7 +530,6 @@ int run_circular(const NbhDesc* d, const float* in, float* out, uint8_t* out_mas
     NBH_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int32_t), st));
     circ_tables_kernel<<<1, 256, 0, st>>>(w.ktab, w.wtab, w.area_const, r, 0);
     const long long npts = (long long)d->ny * d->nx;
-    const size_t gsm = (size_t)(r + 1) * 4;
     if (d->mask2d && !masknd && !(d->flags & NBH_SUM_ONLY)) {
       // area_sum = the same gather applied to the mask (one plane, sum_only)
       circ_mask_to_float_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(d->mask2d, w.maskf, npts);
@@ -445,7 +538,7 @@ int run_circular(const NbhDesc* d, const float* in, float* out, uint8_t* out_mas
       a.cprefix = nullptr; a.plane_stride = npts; a.member_stride = 0; a.n_members = 1; a.n_thr = 1; a.t = 0;
       a.plane0 = 0; a.n_batch = 1; a.flags = NBH_SUM_ONLY; a.thr.mode = 0;
       circ_prefix_kernel<<<(unsigned)((d->ny + 7) / 8), 256, 0, st>>>(a);
-      circ_gather_kernel<<<(unsigned)((npts + 255) / 256), 256, gsm, st>>>(a);
+      if (launch_circ_gather(a, d->ny, d->nx, st)) return 1;
     }
     ProfileScope prof(st);
     for (int t = 0; t < g.n_thr; ++t) {
@@ -457,8 +550,7 @@ int run_circular(const NbhDesc* d, const float* in, float* out, uint8_t* out_mas
         g.n_batch = (int)min((long long)w.batch, d->n_planes - p0);
         const long long rows = (long long)g.n_batch * d->ny;
         circ_prefix_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(g);
-        const long long outs = (long long)g.n_batch * npts;
-        circ_gather_kernel<<<(unsigned)((outs + 255) / 256), 256, gsm, st>>>(g);
+        if (launch_circ_gather(g, d->ny, d->nx, st)) return 1;
       }
     }
     NBH_CHECK_CUDA(cudaGetLastError());
