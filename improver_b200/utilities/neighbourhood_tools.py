@@ -15,43 +15,48 @@ from typing import Any, Tuple, Union
 import numpy as np
 
 
+_TOO_FEW_DIMS = ("Number of dimensions of the input array must be greater than or "
+                 "equal to the length of the neighbourhood shape used for "
+                 "constructing rolling window neighbourhoods.")
+_WINDOW_TOO_BIG = ("The calculated shape of the output array view contains a "
+                   "dimension that is negative or zero. Each dimension of the "
+                   "neighbourhood shape must be less than or equal to the "
+                   "corresponding dimension of the input array.")
+
+
 def rolling_window(input_array: np.ndarray, shape: Tuple[int, int], writeable: bool = False) -> np.ndarray:
-    """neighbourhood_tools.py:13-66."""
-    num_window_dims = len(shape)
-    num_arr_dims = len(input_array.shape)
-    if num_arr_dims < num_window_dims:
-        raise ValueError(
-            "Number of dimensions of the input array must be greater than or "
-            "equal to the length of the neighbourhood shape used for "
-            "constructing rolling window neighbourhoods.")
-    adjshp = (*input_array.shape[:-num_window_dims],
-              *(a - w + 1 for a, w in zip(input_array.shape[-num_window_dims:], shape)),
-              *shape)
-    if any(a <= 0 for a in adjshp):
-        raise RuntimeError(
-            "The calculated shape of the output array view contains a "
-            "dimension that is negative or zero. Each dimension of the "
-            "neighbourhood shape must be less than or equal to the "
-            "corresponding dimension of the input array.")
-    strides = input_array.strides + input_array.strides[-num_window_dims:]
-    return np.lib.stride_tricks.as_strided(input_array, shape=adjshp, strides=strides, writeable=writeable)
+    """Strided view whose trailing `len(shape)` axes enumerate the window around
+    every valid position of the trailing axes of `input_array`
+    (neighbourhood_tools.py:13-66).  No data is copied."""
+    k = len(shape)
+    if input_array.ndim < k:
+        raise ValueError(_TOO_FEW_DIMS)
+    lead, tail = input_array.shape[:-k], input_array.shape[-k:]
+    positions = tuple(n - w + 1 for n, w in zip(tail, shape))
+    view_shape = lead + positions + tuple(shape)
+    if min(view_shape, default=1) <= 0:
+        raise RuntimeError(_WINDOW_TOO_BIG)
+    view_strides = input_array.strides + input_array.strides[-k:]
+    return np.lib.stride_tricks.as_strided(input_array, view_shape, view_strides, writeable=writeable)
 
 
 def pad_and_roll(input_array: np.ndarray, shape: Tuple[int, int], **kwargs: Any) -> np.ndarray:
-    """neighbourhood_tools.py:69-101."""
+    """np.pad the trailing axes by half a window on each side (kwargs go to
+    np.pad) and return the rolling-window view, so that the window axes can be
+    reduced to an array of the original shape (neighbourhood_tools.py:69-101)."""
     writeable = kwargs.pop("writeable", False)
-    pad_extent = [(0, 0)] * (len(input_array.shape) - len(shape))
-    pad_extent.extend((d // 2, d // 2) for d in shape)
-    input_array = np.pad(input_array, pad_extent, **kwargs)
-    return rolling_window(input_array, shape, writeable=writeable)
+    n_lead = input_array.ndim - len(shape)
+    widths = [(0, 0)] * n_lead + [(w // 2, w // 2) for w in shape]
+    return rolling_window(np.pad(input_array, widths, **kwargs), shape, writeable=writeable)
 
 
 def pad_boxsum(data: np.ndarray, boxsize: Union[int, Tuple[int, int]], **pad_options: Any) -> np.ndarray:
-    """neighbourhood_tools.py:104-126 (one extra row/column at the top/left)."""
-    boxsize = np.atleast_1d(boxsize)
-    ih, jh = boxsize[0] // 2, boxsize[-1] // 2
-    padding = [(0, 0)] * (data.ndim - 2) + [(ih + 1, ih), (jh + 1, jh)]
-    return np.pad(data, padding, **pad_options)
+    """Pad for `boxsum`: half a box after, half a box plus one before, on the
+    last two axes (neighbourhood_tools.py:104-126)."""
+    box = np.atleast_1d(boxsize)
+    half_y, half_x = int(box[0]) // 2, int(box[-1]) // 2
+    widths = [(0, 0)] * (data.ndim - 2) + [(half_y + 1, half_y), (half_x + 1, half_x)]
+    return np.pad(data, widths, **pad_options)
 
 
 def boxsum(data: np.ndarray, boxsize: Union[int, Tuple[int, int]], cumsum: bool = True,
