@@ -443,7 +443,7 @@ template <int VEC, int G, int TM, bool M2D>
 static int launch_square_warp_mode(const SqParams& p, const SqWarpGeom& g, cudaStream_t st) {
   constexpr int MBR0 = 16 / (VEC * G) > 0 ? 16 / (VEC * G) : 1;
   constexpr int MBR = MBR0 > kSqHrowRows ? kSqHrowRows : MBR0;
-  constexpr int MBM = 36 / (VEC * G) > 18 ? 18 : 36 / (VEC * G);
+  constexpr int MBM = G == 2 ? 12 / VEC : (36 / VEC > 18 ? 18 : 36 / VEC);   // G == 2: smaller chunks keep 128 registers
   if (p.n_members == 1) return launch_square_warp_one<VEC, G, TM, M2D, true, true, MBR>(p, g, st);
   if (p.n_members % MBM == 0) return launch_square_warp_one<VEC, G, TM, M2D, false, true, MBM>(p, g, st);
   return launch_square_warp_one<VEC, G, TM, M2D, false, false, MBM>(p, g, st);
