@@ -279,6 +279,18 @@ __global__ void __launch_bounds__(256) circ_prefix_kernel(const CircGlobalParams
     atomicOr(reinterpret_cast<unsigned*>(p.status), 1u);
 }
 
+// extended inclusive prefix of a periodic row: E(c) for any c in [-nx, 2nx)
+__device__ __forceinline__ double wrap_prefix(const double* pre, int c, int nx) {
+  const double total = pre[nx - 1];
+  if (c < 0) return pre[c + nx] - total;
+  if (c >= nx) return pre[c - nx] + total;
+  return pre[c];
+}
+
+__device__ __forceinline__ double span_sum_wrap(const double* pre, int x, int w, int nx) {
+  return wrap_prefix(pre, x + w, nx) - wrap_prefix(pre, x - w - 1, nx);
+}
+
 __device__ __forceinline__ double span_sum(const double* pre, int x, int w, int nx) {
   const int lo = max(x - w, 0), hi = min(x + w, nx - 1);
   double s = pre[hi] - (lo > 0 ? pre[lo - 1] : 0.0);
@@ -304,8 +316,13 @@ __global__ void __launch_bounds__(256) circ_gather_kernel(const CircGlobalParams
   for (int dy = -p.r; dy <= p.r; ++dy) {
     const int w = wtab_s[dy < 0 ? -dy : dy];
     const int ys = min(max(y + dy, 0), p.ny - 1);
-    S += span_sum(pre + (long long)ys * p.nx, x, w, p.nx);
-    if (cpre) A += span_sum(cpre + (long long)ys * p.nx, x, w, p.nx);
+    if (p.flags & NBH_WRAP_X) {
+      S += span_sum_wrap(pre + (long long)ys * p.nx, x, w, p.nx);
+      if (cpre) A += span_sum_wrap(cpre + (long long)ys * p.nx, x, w, p.nx);
+    } else {
+      S += span_sum(pre + (long long)ys * p.nx, x, w, p.nx);
+      if (cpre) A += span_sum(cpre + (long long)ys * p.nx, x, w, p.nx);
+    }
   }
   const long long plane = p.plane0 + b;
   const long long o = (plane * p.n_thr + p.t) * per_plane + pt;
@@ -351,7 +368,8 @@ __global__ void __launch_bounds__(256) circ_gather_tiled_kernel(const CircGlobal
     const int jr = i / TC, jc = i - jr * TC;
     const int ys = min(max(y0 - r + jr, 0), p.ny - 1);          // edge replication in y
     const int gc = x0 - r - 1 + jc;
-    tile[i] = gc < 0 ? 0.0 : pre[(long long)ys * p.nx + min(gc, p.nx - 1)];
+    if (p.flags & NBH_WRAP_X) tile[i] = wrap_prefix(pre + (long long)ys * p.nx, gc, p.nx);
+    else tile[i] = gc < 0 ? 0.0 : pre[(long long)ys * p.nx + min(gc, p.nx - 1)];
   }
   __syncthreads();
 
@@ -367,6 +385,7 @@ __global__ void __launch_bounds__(256) circ_gather_tiled_kernel(const CircGlobal
     for (int dy = -r; dy <= r; ++dy) {
       const int w = wtab_s[dy < 0 ? -dy : dy];
       const double* row = tile + (size_t)(ly + r + dy) * TC + cshift;   // indexable by global column >= -1
+      if (p.flags & NBH_WRAP_X) { S += row[x + w] - row[x - w - 1]; continue; }
       const int lo = max(x - w, 0), hi = min(x + w, p.nx - 1);
       double s = row[hi] - row[lo - 1];
       const int nl = lo - (x - w), nr = (x + w) - hi;             // replicated edge cells (mode="nearest")
@@ -502,7 +521,8 @@ int run_circular(const NbhDesc* d, const float* in, float* out, uint8_t* out_mas
   if (validate_desc(d)) return 1;
   NBH_REQUIRE(in && out && status && workspace, "null pointer argument");
   NBH_REQUIRE(workspace_bytes >= circular_workspace_bytes(*d), "workspace too small");
-  NBH_REQUIRE(!(d->flags & NBH_WRAP_X), "wrap_x is not supported for circular neighbourhoods");
+  NBH_REQUIRE(!(d->flags & NBH_WRAP_X) || (use_global_path(*d) && d->nx > 2 * d->cells + 1),
+              "wrap_x needs an unweighted circular neighbourhood narrower than the grid");
   const bool masknd = d->mask_nd != nullptr;
   const bool weighted = (d->flags & NBH_WEIGHTED) != 0;
   const int r = d->cells, nb = 2 * r + 1;
@@ -536,7 +556,7 @@ int run_circular(const NbhDesc* d, const float* in, float* out, uint8_t* out_mas
       CircGlobalParams a = g;
       a.in = w.maskf; a.out = w.area; a.out_mask = nullptr; a.mask2d = nullptr; a.mask_nd = nullptr;
       a.cprefix = nullptr; a.plane_stride = npts; a.member_stride = 0; a.n_members = 1; a.n_thr = 1; a.t = 0;
-      a.plane0 = 0; a.n_batch = 1; a.flags = NBH_SUM_ONLY; a.thr.mode = 0;
+      a.plane0 = 0; a.n_batch = 1; a.flags = NBH_SUM_ONLY | (d->flags & NBH_WRAP_X); a.thr.mode = 0;
       circ_prefix_kernel<<<(unsigned)((d->ny + 7) / 8), 256, 0, st>>>(a);
       if (launch_circ_gather(a, d->ny, d->nx, st)) return 1;
     }

@@ -145,3 +145,22 @@ def test_inf_and_masked_nan_inputs():
     res = orc.neighbourhood(np.ma.masked_array(d2[0], m[0]), None, "square", 2)
     _close(out.cpu().numpy()[0], np.ma.getdata(res))
     np.testing.assert_array_equal(omask.cpu().numpy()[0].astype(bool), np.ma.getmaskarray(res))
+
+
+@pytest.mark.parametrize("cells", [3, 20])
+def test_circular_wrap_x_extension(cells):
+    """Periodic x for circular neighbourhoods (config 5 extension; oracle =
+    reference semantics on the wrap-padded field)."""
+    from improver_b200 import engine
+
+    rng = np.random.default_rng(41 + cells)
+    data = rng.random((2, 70, 96)).astype(np.float32)
+    mask = (rng.random((70, 96)) < 0.8).astype(np.uint8)
+    for m in (None, mask):
+        out, _, st = engine.neighbourhood(_dev(data), cells, method="circular", wrap_x=True,
+                                          mask2d=_dev(m) if m is not None else None)
+        engine.check_status(st)
+        padded = np.pad(data, ((0, 0), (0, 0), (cells, cells)), mode="wrap")
+        pm = np.pad(m, ((0, 0), (cells, cells)), mode="wrap") if m is not None else None
+        exp, _ = orc.neighbourhood_cube(padded, pm, method="circular", cells=cells)
+        _close(out.cpu().numpy(), exp[..., cells:-cells])
