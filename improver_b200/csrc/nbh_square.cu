@@ -12,6 +12,7 @@
 // columns, no synchronisation), and (3) per output row does the horizontal
 // window sum as a difference of a float64 row prefix built with a warp-shuffle
 // scan, normalises by the valid-cell count and stores float32.
+#include "nbh_square_mt.cuh"
 #include "nbh_square_tma.cuh"
 
 namespace nbh {
@@ -491,7 +492,36 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
       }
     }
   }
-  if (use_tma) {
+  // several thresholds on the fused member path: read the input once per group of thresholds
+  SqWarpGeom wgm;
+  const bool use_mt = !use_tma && use_warp && pl.vec >= 2 && d->n_members >= 2 && d->n_thresholds >= 2 &&
+                      tm >= 1 && !(d->flags & NBH_WRAP_X) && env_int("NBH_SQ_MT", 0) &&   // opt-in: see profiles/r1_multi_threshold.jsonl
+                      plan_square_warp(*d, 2, &wgm) && wgm.WS == 64;
+  if (use_mt) {
+    // tasks do not include the threshold index: re-plan the y segmentation for 12 warps / SM
+    const long long units = d->n_planes * (long long)wgm.n_strips;
+    int ysegs = env_int("NBH_SQW_YSEGS", 0);
+    if (ysegs <= 0) {
+      const double slots = (double)sm_count() * 12;
+      const int max_segs = max(1, d->ny / max(32, 6 * d->cells));
+      ysegs = (int)min((double)max_segs, max(1.0, ceil(5.0 * slots / (double)units)));
+    }
+    ysegs = max(1, min(ysegs, d->ny));
+    wgm.seg_rows = (d->ny + ysegs - 1) / ysegs;
+    wgm.n_ysegs = (d->ny + wgm.seg_rows - 1) / wgm.seg_rows;
+    wgm.n_tasks = units * wgm.n_ysegs;
+    wgm.n_sm = 0;
+    ProfileScope prof(st);
+    rc = 0;
+    for (int t0 = 0; t0 < d->n_thresholds && rc == 0; t0 += kMtThresholds) {
+      SqParams pg = p;
+      SqMtParams mt;
+      mt.t_base = t0;
+      mt.n_launch = min(kMtThresholds, d->n_thresholds - t0);
+      for (int i = 0; i < mt.n_launch; ++i) pg.thr.t[i] = p.thr.t[t0 + i];
+      rc = launch_square_mt(pg, wgm, mt, tm_warp, d->mask2d != nullptr, st);
+    }
+  } else if (use_tma) {
     NBH_CHECK_CUDA(cudaMemcpyAsync(w.tmap, &tmap, sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
     ProfileScope prof(st);
     rc = launch_square_tma(p, wg, tg, w.tmap, tm_warp, d->mask2d != nullptr, st);

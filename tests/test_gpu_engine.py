@@ -235,3 +235,24 @@ def test_tma_variant_matches_oracle(shape, monkeypatch):
                                               thresholds=[(2.0, 1.4, 2.6, ">")], collapse_members=True)
         engine.check_status(status)
         _assert_close(out.cpu().numpy(), exp)
+
+
+def test_multi_threshold_variant_matches_oracle(monkeypatch):
+    """Opt-in multi-threshold kernel (NBH_SQ_MT=1): input read once per group of four thresholds."""
+    from improver_b200 import engine
+
+    monkeypatch.setenv("NBH_SQ_MT", "1")
+    rng = np.random.default_rng(33)
+    data = rng.gamma(2.0, 1.5, (5, 2, 48, 70)).astype(np.float32)
+    data[1, 0] = 50.0                                        # an all-ones member (edge flags)
+    data[1, 0, :2, 4:9] = 0.1
+    thr = [0.5, 1.0, 2.0, 4.0, 6.0]
+    bounds = orc.fuzzy_bounds_from_factor(thr, 0.7)
+    mask = (rng.random((48, 70)) < 0.8).astype(np.uint8)
+    for m in (None, mask):
+        exp = orc.threshold_square_mean(data, thr, bounds, ">", 3, mask=m)
+        out, _, status = engine.neighbourhood(_dev(data), 3, mask2d=_dev(m) if m is not None else None,
+                                              thresholds=[(t, b[0], b[1], ">") for t, b in zip(thr, bounds)],
+                                              collapse_members=True)
+        engine.check_status(status)
+        _assert_close(out.cpu().numpy(), exp)
