@@ -14,6 +14,7 @@
 // scan, normalises by the valid-cell count and stores float32.
 #include "nbh_square_mt.cuh"
 #include "nbh_square_tma.cuh"
+#include "nbh_square_rs.cuh"
 
 namespace nbh {
 
@@ -332,6 +333,8 @@ static bool plan_square_warp(const NbhDesc& d, int vec, SqWarpGeom* g) {
   return true;
 }
 
+bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid);
+
 bool make_square_tensor_map(const float* in, int ny, int nx, long long n_planes, int n_members,
                             long long plane_stride, long long member_stride, int box_cols, CUtensorMap* map,
                             int* super_rows);
@@ -497,7 +500,13 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   const bool use_mt = !use_tma && use_warp && pl.vec >= 2 && d->n_members >= 2 && d->n_thresholds >= 2 &&
                       tm >= 1 && !(d->flags & NBH_WRAP_X) && env_int("NBH_SQ_MT", 0) &&   // opt-in: see profiles/r1_multi_threshold.jsonl
                       plan_square_warp(*d, 2, &wgm) && wgm.WS == 64;
-  if (use_mt) {
+  SqRsGeom rg;
+  int rs_grid = 0;
+  const bool use_rs = use_warp && !use_tma && !use_mt && plan_square_rs(*d, in, &rg, &rs_grid);
+  if (use_rs) {
+    ProfileScope prof(st);
+    rc = launch_square_rs(p, rg, tm_warp, d->mask2d != nullptr, rs_grid, st);
+  } else if (use_mt) {
     // tasks do not include the threshold index: re-plan the y segmentation for 12 warps / SM
     const long long units = d->n_planes * (long long)wgm.n_strips;
     int ysegs = env_int("NBH_SQW_YSEGS", 0);

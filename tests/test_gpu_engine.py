@@ -256,3 +256,42 @@ def test_multi_threshold_variant_matches_oracle(monkeypatch):
                                               collapse_members=True)
         engine.check_status(status)
         _assert_close(out.cpu().numpy(), exp)
+
+
+@pytest.mark.parametrize("shape,cells", [((6, 3, 97, 130), 5), ((18, 2, 64, 1042), 5), ((7, 4, 33, 58), 2),
+                                         ((4, 5, 120, 64), 1), ((12, 2, 51, 700), 9)])
+def test_row_stream_kernel_matches_oracle_and_warp_kernel(shape, cells, monkeypatch):
+    """Row-streaming fused square kernel (bulk-copy staged full rows, default for
+    the fused member path): oracle parity with and without an external mask, several
+    thresholds, an all-ones member with an edge blob (trimming fix-up flags), shares
+    that straddle planes, and equality with the warp kernel it replaces (NBH_SQ_RS=0)."""
+    from improver_b200 import engine
+
+    rng = np.random.default_rng(41)
+    data = rng.gamma(2.0, 1.5, shape).astype(np.float32)
+    data[1, 0] = 50.0                                        # truth value 1 everywhere ...
+    data[1, 0, :2, 4:9] = 0.1                                # ... except an edge blob
+    data[2, -1] = 50.0
+    data[2, -1, 10:12, -3:] = 0.0
+    thr = [1.0, 2.0, 4.0]
+    bounds = list(orc.fuzzy_bounds_from_factor(thr, 0.7))
+    bounds[2] = (3.0, 6.5)                                   # asymmetric bounds: general two-slope form
+    tl = [(t, b[0], b[1], ">") for t, b in zip(thr, bounds)]
+    mask = (rng.random(shape[2:]) < 0.8).astype(np.uint8)
+    for m in (None, mask):
+        md = _dev(m) if m is not None else None
+        monkeypatch.setenv("NBH_SQ_RS", "1")
+        out, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, thresholds=tl, collapse_members=True)
+        engine.check_status(status)
+        exp = orc.threshold_square_mean(data, thr, bounds, ">", cells, mask=m)
+        _assert_close(out.cpu().numpy(), exp)
+        monkeypatch.setenv("NBH_SQ_RS", "0")
+        ref, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, thresholds=tl, collapse_members=True)
+        engine.check_status(status)
+        np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), atol=2e-7, equal_nan=True)
+    # deterministic comparison and raw-data (no threshold) member means
+    monkeypatch.setenv("NBH_SQ_RS", "1")
+    out, _, status = engine.neighbourhood(_dev(data), cells, thresholds=[(2.0, 2.0, 2.0, ">=")],
+                                          collapse_members=True)
+    engine.check_status(status)
+    _assert_close(out.cpu().numpy(), orc.threshold_square_mean(data, [2.0], [(2.0, 2.0)], ">=", cells))
