@@ -225,6 +225,7 @@ def run_ours(args):
 
     # ---- dominant kernel duration (roofline) --------------------------------
     kernel_ms = pipeline.time_main_kernel(lambda: step(), reps=max(3, args.steps))
+    kernel_name = pipeline.last_profiled_kernel()
     peak, peak_src = peaks()
     achieved = ALGO_BYTES_PER_STEP / (kernel_ms * 1e-3) / 1e9
 
@@ -270,7 +271,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_8TBs": achieved / 8000.0,
                          "traffic": pipeline.recorded_traffic_bytes(),
-                         "kernel": "nbh::square_warp_kernel<VEC=2,G=1,TM=fuzzy,M2D=0,ROWS=0,FULL=1,MB=18>",
+                         "kernel": kernel_name,
                          "kernel_ms": kernel_ms,
                          "algorithmic_bytes": ALGO_BYTES_PER_STEP, "peak_source": peak_src},
             "hbm_gbs": achieved,

@@ -71,6 +71,8 @@ def load() -> C.CDLL:
                                       C.c_void_p, C.c_void_p]
     lib.nbh_profile_enable.argtypes = [C.c_int]
     lib.nbh_profile_last_ms.argtypes = [C.POINTER(C.c_float)]
+    lib.nbh_profile_last_kernel.restype = C.c_char_p
+    lib.nbh_profile_last_kernel.argtypes = []
     if lib.nbh_version() != 1:
         raise ImportError("libimprover_b200.so ABI version mismatch")
     _lib = lib
@@ -86,4 +88,4 @@ def check(rc: int) -> None:
 EXPORTED = ["nbh_version", "nbh_last_error", "nbh_device_info", "nbh_workspace_bytes",
             "nbh_square_f32", "nbh_circular_f32", "nbh_percentiles_f32",
             "nbh_percentiles_workspace_bytes", "nbh_threshold_f32",
-            "nbh_profile_enable", "nbh_profile_last_ms"]
+            "nbh_profile_enable", "nbh_profile_last_ms", "nbh_profile_last_kernel"]

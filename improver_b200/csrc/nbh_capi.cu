@@ -19,9 +19,11 @@ void set_error(const char* fmt, ...) {
 static bool g_prof_on = false;
 static cudaEvent_t g_prof_e0 = nullptr, g_prof_e1 = nullptr;
 static bool g_prof_valid = false;
+static const char* g_prof_name = "";
 
-ProfileScope::ProfileScope(cudaStream_t s) : st(s), on(g_prof_on) {
+ProfileScope::ProfileScope(cudaStream_t s, const char* name) : st(s), on(g_prof_on) {
   if (!on) return;
+  g_prof_name = name;
   if (!g_prof_e0) { cudaEventCreate(&g_prof_e0); cudaEventCreate(&g_prof_e1); }
   cudaEventRecord(g_prof_e0, st);
 }
@@ -182,6 +184,8 @@ int nbh_profile_last_ms(float* ms) {
   NBH_CHECK_CUDA(cudaEventElapsedTime(ms, nbh::g_prof_e0, nbh::g_prof_e1));
   return 0;
 }
+
+const char* nbh_profile_last_kernel(void) { return nbh::g_prof_name; }
 
 int nbh_device_info(int32_t* sm_count, int64_t* smem_optin_bytes) {
   int dev = 0, n = 0, s = 0;

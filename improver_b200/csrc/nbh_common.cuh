@@ -205,7 +205,7 @@ template <> struct VecLoad<4> {
 struct ProfileScope {
   cudaStream_t st;
   bool on;
-  explicit ProfileScope(cudaStream_t s);
+  explicit ProfileScope(cudaStream_t s, const char* name = "");
   ~ProfileScope();
 };
 

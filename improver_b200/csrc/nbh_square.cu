@@ -504,7 +504,7 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   int rs_grid = 0;
   const bool use_rs = use_warp && !use_tma && !use_mt && plan_square_rs(*d, in, &rg, &rs_grid);
   if (use_rs) {
-    ProfileScope prof(st);
+    ProfileScope prof(st, "nbh::square_rs_kernel (row-streaming, bulk-copy staged rows)");
     rc = launch_square_rs(p, rg, tm_warp, d->mask2d != nullptr, rs_grid, st);
   } else if (use_mt) {
     // tasks do not include the threshold index: re-plan the y segmentation for 12 warps / SM
@@ -520,7 +520,7 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
     wgm.n_ysegs = (d->ny + wgm.seg_rows - 1) / wgm.seg_rows;
     wgm.n_tasks = units * wgm.n_ysegs;
     wgm.n_sm = 0;
-    ProfileScope prof(st);
+    ProfileScope prof(st, "nbh::square_mt_kernel");
     rc = 0;
     for (int t0 = 0; t0 < d->n_thresholds && rc == 0; t0 += kMtThresholds) {
       SqParams pg = p;
@@ -532,10 +532,10 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
     }
   } else if (use_tma) {
     NBH_CHECK_CUDA(cudaMemcpyAsync(w.tmap, &tmap, sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
-    ProfileScope prof(st);
+    ProfileScope prof(st, "nbh::square_tma_kernel");
     rc = launch_square_tma(p, wg, tg, w.tmap, tm_warp, d->mask2d != nullptr, st);
   } else if (use_warp) {
-    ProfileScope prof(st);
+    ProfileScope prof(st, "nbh::square_warp_kernel (warp-autonomous strips)");
     const bool m2d = d->mask2d != nullptr;
     switch (pl.vec) {
       case 4: rc = launch_square_warp_vec<4>(p, wg, tm_warp, m2d, st); break;
@@ -543,7 +543,7 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
       default: rc = launch_square_warp_vec<1>(p, wg, tm_warp, m2d, st); break;
     }
   } else {
-    ProfileScope prof(st);
+    ProfileScope prof(st, "nbh::square_kernel (block-cooperative strips)");
     const bool m2d = d->mask2d != nullptr;
     switch (pl.vec) {
       case 4: rc = launch_square_vec<4>(p, pl, blocks, tm, masknd, m2d, st); break;

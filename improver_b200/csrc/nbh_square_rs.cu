@@ -47,6 +47,7 @@ bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid) {
   while (shift < 22 && (double)nb * nb * R * (double)(1u << (shift + 1)) < 2147483648.0) ++shift;
   if (d.n_thresholds > 0 && shift < 12) return false;   // huge windows: keep the float64 kernels
   g->fx_shift = shift;
+  g->wait_ns = (unsigned)env_int("NBH_SQ_RS_WAIT_NS", 1000);
   g->rows_total = d.n_planes * (long long)max(d.n_thresholds, 1) * d.ny;
   // one block per SM; every share at least ~4r rows so the y halo stays a minor cost
   const long long min_share = max(16, 4 * r);

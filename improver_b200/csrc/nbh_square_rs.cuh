@@ -49,12 +49,33 @@ struct SqRsGeom {
   long long rows_total; // n_units * ny
   long long share;      // rows per block
   int fx_shift;         // fixed-point scale of the thresholded member sums (2^fx_shift)
+  unsigned wait_ns;     // suspend-time hint of the barrier waits
 };
 
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// try_wait with a suspend-time hint: a waiting thread sleeps in hardware instead of spinning
+// through the issue port (the producers wait most of the time, the consumers some of it)
+__device__ __forceinline__ void mbar_wait_hint(unsigned bar, unsigned parity, unsigned hint_ns) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "NBH_WAITH_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra NBH_DONEH_%=;\n"
+      "bra NBH_WAITH_%=;\n"
+      "NBH_DONEH_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+}
+__device__ __forceinline__ float2 lds_f2(unsigned addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
 }
 
 // the share of block b as a sequence of pieces (unit, ya, yb), in marching order
@@ -136,7 +157,7 @@ square_rs_kernel(const __grid_constant__ SqParams p, const SqRsGeom g) {
         const unsigned bytes = (shift_b + (unsigned)p.nx * 4u + 15u) & ~15u;
         const char* src = reinterpret_cast<const char*>(row) - shift_b;
         for (int m0 = 0; m0 < R; m0 += MS) {
-          mbar_wait(empty0 + 8 * s, (round & 1u) ^ 1u);
+          mbar_wait_hint(empty0 + 8 * s, (round & 1u) ^ 1u, g.wait_ns);
           mbar_expect_tx(full0 + 8 * s, bytes * (unsigned)n_mine);
           unsigned dst = stage0 + (unsigned)s * stage_bytes + (unsigned)(pw * g.pitch) * 4u;
           const char* q = src + (long long)(m0 + pw) * p.member_stride * 4;
@@ -200,10 +221,16 @@ square_rs_kernel(const __grid_constant__ SqParams p, const SqRsGeom g) {
   const double inv_members_fx = p.inv_members * fx_inv;
   if (lane == 0) { hrow[0] = 0.0; }                 // also zeroes hrow_u[0]
 
-  const int pitch = g.pitch;
+  const unsigned pitch_b = (unsigned)g.pitch * 4u;
+  const unsigned stage_lane0 = smem_u32(stages) + (unsigned)gx * 4u;    // this lane's column in stage 0
   float nanacc = 0.f;
+  // stage cursor: barrier address, this lane's address in the stage, phase parity
   int s = 0;
-  unsigned round = 0;
+  unsigned parity = 0, bar = full0, st_addr = stage_lane0;
+  auto next_stage = [&]() {
+    bar += 8; st_addr += stage_bytes;
+    if (++s == NS) { s = 0; parity ^= 1u; bar = full0; st_addr = stage_lane0; }
+  };
   RsPieces pieces(g.share, g.rows_total, p.ny, blockIdx.x);
   long long unit; int ya, yb;
   while (pieces.next(&unit, &ya, &yb)) {
@@ -241,35 +268,35 @@ square_rs_kernel(const __grid_constant__ SqParams p, const SqRsGeom g) {
         const bool row_band = yy <= r || yy >= p.ny - 1 - r;
         const bool flagged = !sum_only && (need_cols || row_band);
         const bool v0 = !M2D || (m2_cur & 0xffu), v1 = !M2D || (m2_cur & 0xff00u);
-        const int lane_off = shift + gx;
+        const unsigned shift_b = (unsigned)shift * 4u;
         if (!flagged) {
           for (int m0 = 0; m0 < R; m0 += MS) {
-            mbar_wait(full0 + 8 * s, round & 1u);
-            const float* q = stages + (size_t)s * (stage_bytes >> 2) + lane_off;
+            mbar_wait_hint(bar, parity, g.wait_ns);
+            unsigned q = st_addr + shift_b;
 #pragma unroll 3
             for (int j = 0; j < MS; ++j) {
-              const float2 d = *reinterpret_cast<const float2*>(q);
-              q += pitch;
+              const float2 d = lds_f2(q);
+              q += pitch_b;
               nanacc = max_nan(nanacc, fabsf(d.x));
               nanacc = max_nan(nanacc, fabsf(d.y));
               acc0 += truth_value_sum<TM>(d.x, thr);
               acc1 += truth_value_sum<TM>(d.y, thr);
             }
             __syncwarp();                                  // every lane has read stage s
-            if (lane == 0) mbar_arrive(empty0 + 8 * s);
-            if (++s == NS) { s = 0; ++round; }
+            if (lane == 0) mbar_arrive(bar + 8 * kRsMaxStages);
+            next_stage();
           }
           if (M2D) { acc0 = v0 ? acc0 : 0.f; acc1 = v1 ? acc1 : 0.f; }   // the mask is shared by all members
         } else {
           unsigned long long ne = 0;
           for (int m0 = 0; m0 < R; m0 += MS) {
-            mbar_wait(full0 + 8 * s, round & 1u);
-            const float* q = stages + (size_t)s * (stage_bytes >> 2) + lane_off;
+            mbar_wait_hint(bar, parity, g.wait_ns);
+            unsigned q = st_addr + shift_b;
             unsigned long long bit = 1ull << m0;
 #pragma unroll 2
             for (int j = 0; j < MS; ++j) {
-              const float2 d = *reinterpret_cast<const float2*>(q);
-              q += pitch;
+              const float2 d = lds_f2(q);
+              q += pitch_b;
               nanacc = max_nan(nanacc, fabsf(d.x));
               nanacc = max_nan(nanacc, fabsf(d.y));
               acc0 += truth_value_sum<TM>(d.x, thr);
@@ -278,8 +305,8 @@ square_rs_kernel(const __grid_constant__ SqParams p, const SqRsGeom g) {
               bit <<= 1;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * s);
-            if (++s == NS) { s = 0; ++round; }
+            if (lane == 0) mbar_arrive(bar + 8 * kRsMaxStages);
+            next_stage();
           }
           if (M2D) { acc0 = v0 ? acc0 : 0.f; acc1 = v1 ? acc1 : 0.f; }
           if (!v0 || !v1) ne = all_members;                // a masked cell counts as "not one" for every member
@@ -326,8 +353,8 @@ square_rs_kernel(const __grid_constant__ SqParams p, const SqRsGeom g) {
         unsigned incl = s1;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-          const unsigned o2 = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += o2;
+          asm volatile("{\n.reg .pred p;\n.reg .u32 t;\nshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n@p add.u32 %0, %0, t;\n}\n"
+                       : "+r"(incl) : "r"(d));
         }
         const unsigned excl = incl - s1;
         *reinterpret_cast<uint2*>(hrow_u + c0 + 2) = make_uint2(excl + U0, excl + s1);   // prefix[c0 + 1], [c0 + 2] at +1

@@ -118,6 +118,11 @@ def time_main_kernel(fn, reps: int = 5) -> float:
     return total / reps
 
 
+def last_profiled_kernel() -> str:
+    """Name of the kernel bracketed by the last profiled native call."""
+    return _lib.load().nbh_profile_last_kernel().decode("utf-8", "replace")
+
+
 def recorded_traffic_bytes():
     """DRAM bytes per launch of the dominant kernel from the committed ncu
     capture (profiles/roofline.json), or None if no capture has been made."""

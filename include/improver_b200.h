@@ -125,6 +125,8 @@ int nbh_threshold_f32(const float* in, const uint8_t* mask_nd, float* out, int32
  * synchronises on those events and returns the kernel's duration. */
 int nbh_profile_enable(int on);
 int nbh_profile_last_ms(float* ms);
+/* name of the kernel that was bracketed (static string, "" if none) */
+const char* nbh_profile_last_kernel(void);
 
 #ifdef __cplusplus
 }
