@@ -15,6 +15,7 @@
 #include "nbh_square_mt.cuh"
 #include "nbh_square_tma.cuh"
 #include "nbh_square_rs.cuh"
+#include "nbh_square_rr.cuh"
 
 namespace nbh {
 
@@ -334,6 +335,7 @@ static bool plan_square_warp(const NbhDesc& d, int vec, SqWarpGeom* g) {
 }
 
 bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid);
+bool plan_square_rr(const NbhDesc& d, const float* in, int tm, SqRrGeom* g, int* grid, size_t* smem);
 
 bool make_square_tensor_map(const float* in, int ny, int nx, long long n_planes, int n_members,
                             long long plane_stride, long long member_stride, int box_cols, CUtensorMap* map,
@@ -503,9 +505,17 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   SqRsGeom rg;
   int rs_grid = 0;
   const bool use_rs = use_warp && !use_tma && !use_mt && plan_square_rs(*d, in, &rg, &rs_grid);
+  SqRrGeom rrg;
+  int rr_grid = 0;
+  size_t rr_smem = 0;
+  const bool use_rr = !use_rs && !use_tma && !use_mt && !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 &&
+                      plan_square_rr(*d, in, tm_warp, &rrg, &rr_grid, &rr_smem);
   if (use_rs) {
     ProfileScope prof(st, "nbh::square_rs_kernel (row-streaming, bulk-copy staged rows)");
     rc = launch_square_rs(p, rg, tm_warp, d->mask2d != nullptr, rs_grid, st);
+  } else if (use_rr) {
+    ProfileScope prof(st, "nbh::square_rr_kernel (row-streaming, single-member slices)");
+    rc = launch_square_rr(p, rrg, tm_warp, d->mask2d != nullptr, rr_grid, rr_smem, st);
   } else if (use_mt) {
     // tasks do not include the threshold index: re-plan the y segmentation for 12 warps / SM
     const long long units = d->n_planes * (long long)wgm.n_strips;

@@ -295,3 +295,59 @@ def test_row_stream_kernel_matches_oracle_and_warp_kernel(shape, cells, monkeypa
                                           collapse_members=True)
     engine.check_status(status)
     _assert_close(out.cpu().numpy(), orc.threshold_square_mean(data, [2.0], [(2.0, 2.0)], ">=", cells))
+
+
+def _square_oracle_stack(data, mask, cells, wrap=False, sum_only=False):
+    outs = []
+    for sl in data.reshape((-1,) + data.shape[-2:]):
+        if wrap:
+            padded = np.pad(sl, ((0, 0), (cells, cells)), mode="wrap")
+            pm = np.pad(mask, ((0, 0), (cells, cells)), mode="wrap") if mask is not None else None
+            res = orc.neighbourhood(padded, pm, method="square", cells=cells, sum_only=sum_only, re_mask=False)
+            outs.append(np.ma.getdata(res)[:, cells:-cells])
+        else:
+            res = orc.neighbourhood(sl, mask, method="square", cells=cells, sum_only=sum_only, re_mask=False)
+            outs.append(np.ma.getdata(res))
+    return np.stack(outs).reshape(data.shape)
+
+
+@pytest.mark.parametrize("shape,cells,wrap", [((5, 97, 130), 5, False), ((3, 40, 1042), 5, False),
+                                              ((2, 3, 33, 58), 2, False), ((7, 64, 64), 1, False),
+                                              ((2, 30, 1400), 3, False), ((3, 50, 256), 5, True),
+                                              ((2, 24, 1480), 4, True), ((4, 51, 700), 9, False)])
+def test_row_stream_rows_kernel_matches_oracle(shape, cells, wrap, monkeypatch):
+    """Row-streaming kernel for single-member slices (default un-fused square path):
+    oracle parity with / without an external mask, sum_only, periodic x, x panels
+    (nx > 12 windows), ones-trimming slices, and equality with the warp kernel."""
+    from improver_b200 import engine
+
+    rng = np.random.default_rng(43)
+    data = rng.random(shape).astype(np.float32)
+    flat = data.reshape((-1,) + shape[-2:])
+    if not wrap:      # ones-trimming near the x edges has no defined meaning on a periodic axis
+        flat[0] = 1.0                                        # all ones apart from an edge blob
+        flat[0, :2, 4:9] = 0.25
+        flat[-1] = 1.0
+        flat[-1, 10:12, -3:] = 0.0
+    mask = (rng.random(shape[-2:]) < 0.8).astype(np.uint8)
+    for m in (None, mask):
+        md = _dev(m) if m is not None else None
+        for sum_only in (False, True):
+            monkeypatch.setenv("NBH_SQ_RR", "1")
+            out, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, sum_only=sum_only, wrap_x=wrap)
+            engine.check_status(status)
+            monkeypatch.setenv("NBH_SQ_RR", "0")
+            ref, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, sum_only=sum_only, wrap_x=wrap)
+            engine.check_status(status)
+            scale = max(1.0, float((2 * cells + 1) ** 2)) if sum_only else 1.0
+            np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), atol=2e-6 * scale, equal_nan=True)
+            exp = _square_oracle_stack(data, m, cells, wrap=wrap, sum_only=sum_only)
+            _assert_close(out.cpu().numpy(), exp, atol=ATOL * scale)
+    # thresholded single slices (fixed-point sums) against the oracle chain with one member
+    monkeypatch.setenv("NBH_SQ_RR", "1")
+    if not wrap:
+        gam = rng.gamma(2.0, 1.5, (1,) + flat.shape).astype(np.float32)
+        out, _, status = engine.neighbourhood(_dev(gam[0]), cells, thresholds=[(2.0, 1.4, 2.6, ">")])
+        engine.check_status(status)
+        exp = orc.threshold_square_mean(gam, [2.0], [(1.4, 2.6)], ">", cells)
+        _assert_close(out.cpu().numpy()[:, 0], exp[:, 0])
