@@ -16,8 +16,20 @@ struct ThrParams {
   ThrSet thr;
 };
 
-template <int VEC, int TM, int T>
+constexpr int kThrRcpTable = 256;     // reciprocals 1/k kept in shared memory for k <= 256 collapsed members
+
+// COLLAPSE == false: one contribution per point (no coordinate collapsed), the mean is the value.
+// COLLAPSE == true: np.divide(float32 sum, int64 count) evaluated in float64 and stored as
+// float32 (threshold.py:707).  The float64 quotient is formed without a division instruction
+// sequence: q0 = a * RN(1/c), rem = fma(-q0, c, a), q = fma(rem, RN(1/c), q0) is the correctly
+// rounded a / c (Markstein), with RN(1/c) from a per-block table.
+template <int VEC, int TM, int T, bool COLLAPSE>
 __global__ void __launch_bounds__(256) threshold_kernel(const ThrParams p) {
+  __shared__ double rcp_tab[COLLAPSE ? kThrRcpTable + 1 : 1];
+  if (COLLAPSE) {
+    for (int k = threadIdx.x; k <= kThrRcpTable; k += blockDim.x) rcp_tab[k] = k ? 1.0 / (double)k : 0.0;
+    __syncthreads();
+  }
   const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (i0 >= p.n_points) return;
   float acc[T][VEC];
@@ -54,9 +66,17 @@ __global__ void __launch_bounds__(256) threshold_kernel(const ThrParams p) {
     float o[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      // np.divide(float32, int64) -> float64 -> float32 store; a count of 1 (no
-      // collapse) is the identity
-      o[v] = cnt[v] > 1 ? (float)((double)acc[t][v] / (double)cnt[v]) : (cnt[v] ? acc[t][v] : 0.f);
+      if (!COLLAPSE) {
+        o[v] = cnt[v] ? acc[t][v] : 0.f;
+      } else if (cnt[v] <= 1) {
+        o[v] = cnt[v] ? acc[t][v] : 0.f;          // a count of 1 is the identity
+      } else if (cnt[v] <= kThrRcpTable) {
+        const double a = (double)acc[t][v], c = (double)cnt[v], rc = rcp_tab[cnt[v]];
+        const double q0 = a * rc;
+        o[v] = (float)fma(fma(-q0, c, a), rc, q0);
+      } else {
+        o[v] = (float)((double)acc[t][v] / (double)cnt[v]);
+      }
     }
     VecLoad<VEC>::st(p.out + (long long)t * p.n_points + i0, o);
   }
@@ -66,18 +86,24 @@ __global__ void __launch_bounds__(256) threshold_kernel(const ThrParams p) {
   }
 }
 
+template <int VEC, int TM, bool COLLAPSE>
+static void launch_threshold_c(const ThrParams& p, int n, unsigned blocks, cudaStream_t st) {
+  switch (n) {
+    case 1: threshold_kernel<VEC, TM, 1, COLLAPSE><<<blocks, 256, 0, st>>>(p); break;
+    case 2: threshold_kernel<VEC, TM, 2, COLLAPSE><<<blocks, 256, 0, st>>>(p); break;
+    case 3: threshold_kernel<VEC, TM, 3, COLLAPSE><<<blocks, 256, 0, st>>>(p); break;
+    case 4: threshold_kernel<VEC, TM, 4, COLLAPSE><<<blocks, 256, 0, st>>>(p); break;
+    case 5: threshold_kernel<VEC, TM, 5, COLLAPSE><<<blocks, 256, 0, st>>>(p); break;
+    case 6: threshold_kernel<VEC, TM, 6, COLLAPSE><<<blocks, 256, 0, st>>>(p); break;
+    case 7: threshold_kernel<VEC, TM, 7, COLLAPSE><<<blocks, 256, 0, st>>>(p); break;
+    default: threshold_kernel<VEC, TM, 8, COLLAPSE><<<blocks, 256, 0, st>>>(p); break;
+  }
+}
+
 template <int VEC, int TM>
 static void launch_threshold_t(const ThrParams& p, int n, unsigned blocks, cudaStream_t st) {
-  switch (n) {
-    case 1: threshold_kernel<VEC, TM, 1><<<blocks, 256, 0, st>>>(p); break;
-    case 2: threshold_kernel<VEC, TM, 2><<<blocks, 256, 0, st>>>(p); break;
-    case 3: threshold_kernel<VEC, TM, 3><<<blocks, 256, 0, st>>>(p); break;
-    case 4: threshold_kernel<VEC, TM, 4><<<blocks, 256, 0, st>>>(p); break;
-    case 5: threshold_kernel<VEC, TM, 5><<<blocks, 256, 0, st>>>(p); break;
-    case 6: threshold_kernel<VEC, TM, 6><<<blocks, 256, 0, st>>>(p); break;
-    case 7: threshold_kernel<VEC, TM, 7><<<blocks, 256, 0, st>>>(p); break;
-    default: threshold_kernel<VEC, TM, 8><<<blocks, 256, 0, st>>>(p); break;
-  }
+  if (p.n_collapse > 1) launch_threshold_c<VEC, TM, true>(p, n, blocks, st);
+  else launch_threshold_c<VEC, TM, false>(p, n, blocks, st);
 }
 
 template <int VEC>
