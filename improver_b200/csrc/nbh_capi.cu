@@ -160,6 +160,10 @@ size_t circular_workspace_bytes(const NbhDesc&);
 int run_percentiles(const float*, float*, const float*, int, long long, int, int, int, int32_t*, void*,
                     size_t, cudaStream_t);
 size_t percentiles_workspace_bytes(long long, int, int, int);
+int run_threshold_vicinity(const float* in, const uint8_t* mask_nd, const uint8_t* landmask, float* out,
+                           int32_t* contrib, const NbhThreshold* thresholds, int n_thresholds,
+                           const int32_t* vicinity_cells, int n_vicinity, long long n_collapse,
+                           long long n_planes, int ny, int nx, int32_t* status, cudaStream_t st);
 int run_threshold(const float*, const uint8_t*, float*, int32_t*, const NbhThreshold*, int, long long,
                   long long, int32_t*, cudaStream_t);
 
@@ -232,6 +236,15 @@ int nbh_threshold_f32(const float* in, const uint8_t* mask_nd, float* out, int32
                       int64_t n_points, int32_t* status, void* stream) {
   return nbh::run_threshold(in, mask_nd, out, contrib, thresholds, n_thresholds, n_collapse, n_points,
                             status, static_cast<cudaStream_t>(stream));
+}
+
+int nbh_threshold_vicinity_f32(const float* in, const uint8_t* mask_nd, const uint8_t* landmask, float* out,
+                               int32_t* contrib, const NbhThreshold* thresholds, int32_t n_thresholds,
+                               const int32_t* vicinity_cells, int32_t n_vicinity, int64_t n_collapse,
+                               int64_t n_planes, int32_t ny, int32_t nx, int32_t* status, void* stream) {
+  return nbh::run_threshold_vicinity(in, mask_nd, landmask, out, contrib, thresholds, n_thresholds,
+                                     vicinity_cells, n_vicinity, n_collapse, n_planes, ny, nx, status,
+                                     static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -220,6 +220,56 @@ def threshold(data: torch.Tensor, thresholds, mask_nd: Optional[torch.Tensor] = 
     return out, contrib, status
 
 
+def threshold_vicinity(data: torch.Tensor, thresholds, vicinity_cells: Sequence[int],
+                       mask_nd: Optional[torch.Tensor] = None, landmask: Optional[torch.Tensor] = None,
+                       collapse_leading: bool = False):
+    """Maximum-in-vicinity truth values (threshold.py:473-518, spatial.py:740-855).
+
+    data            float32 CUDA (..., ny, nx); with collapse_leading the leading axis is
+                    averaged over its unmasked members after the vicinity maximum.
+    vicinity_cells  radii in grid cells (square maximum of side 2 r + 1, edges replicated).
+    landmask        uint8/bool (ny, nx), non-zero = land: land and sea are spread separately.
+    Returns (out float32 (V, T, ..., ny, nx), contrib int32 (..., ny, nx), status)."""
+    lib = _lib.load()
+    _require_cuda(data, "data")
+    if data.dtype != torch.float32:
+        raise TypeError("data must be float32")
+    if data.dim() < 2 + (1 if collapse_leading else 0):
+        raise ValueError("data must have (y, x) axes" + (" after the collapsed axis" if collapse_leading else ""))
+    data = data.contiguous()
+    if collapse_leading:
+        n_collapse, pshape = int(data.shape[0]), tuple(int(s) for s in data.shape[1:])
+    else:
+        n_collapse, pshape = 1, tuple(int(s) for s in data.shape)
+    ny, nx = pshape[-2], pshape[-1]
+    n_planes = int(np.prod(pshape[:-2])) if len(pshape) > 2 else 1
+    thr_list = list(thresholds)
+    cells = np.asarray([int(c) for c in vicinity_cells], dtype=np.int32)
+    if cells.size == 0 or not thr_list:
+        raise ValueError("at least one threshold and one vicinity radius are needed")
+    out = torch.empty((len(cells), len(thr_list)) + pshape, dtype=torch.float32, device=data.device)
+    contrib = torch.empty(pshape, dtype=torch.int32, device=data.device)
+    status = torch.zeros(2, dtype=torch.int32, device=data.device)
+    if mask_nd is not None:
+        _require_cuda(mask_nd, "mask_nd")
+        mask_nd = (mask_nd != 0).to(torch.uint8).contiguous()
+    if landmask is not None:
+        _require_cuda(landmask, "landmask")
+        if tuple(landmask.shape) != (ny, nx):
+            raise ValueError("landmask must have the (y, x) shape of the data")
+        landmask = (landmask != 0).to(torch.uint8).contiguous()
+    with torch.cuda.device(data.device):
+        # the native call takes any number of thresholds; build the array in chunks the
+        # helper supports and pass them in one go
+        arr = make_thresholds(thr_list)
+        _lib.check(lib.nbh_threshold_vicinity_f32(
+            data.data_ptr(), mask_nd.data_ptr() if mask_nd is not None else None,
+            landmask.data_ptr() if landmask is not None else None, out.data_ptr(), contrib.data_ptr(),
+            arr, len(thr_list), cells.ctypes.data_as(C.POINTER(C.c_int32)), len(cells), n_collapse, n_planes,
+            ny, nx, status.data_ptr(), _stream_ptr()))
+    return out, contrib, status
+
+
 def neighbourhood_percentiles(data: torch.Tensor, cells: int, percentiles: Sequence[float]):
     """Percentiles of the circular neighbourhood of every point
     (nbhood.py:649-667).  data float32 (..., ny, nx) -> (..., P, ny, nx)."""

@@ -2,8 +2,9 @@
 backed by the CUDA threshold kernel (nbh_threshold_f32).
 
 Constructor arguments, validation order, error types and messages follow
-improver/threshold.py:47-239; `process` follows :571-755.  Vicinity
-processing and unit conversion of the data are "next" rows of the scope table
+improver/threshold.py:47-239; `process` follows :571-755, including maximum-in-
+vicinity processing (:473-518, one fused CUDA launch: nbh_threshold_vicinity_f32).
+Unit conversion of the data and percentile rebadging are outside the hot path
  and raise NotImplementedError.
 """
 from __future__ import annotations
@@ -177,8 +178,6 @@ class Threshold(PostProcessingPlugin):
                              f"input_cube_coords: {input_cube_crds}")
         if self.vicinity is None and landmask is not None:
             raise ValueError("Cannot apply land-mask cube without in-vicinity processing")
-        if self.vicinity is not None:
-            raise NotImplementedError("vicinity processing is outside the CUDA hot path (SURVEY.md §8f)")
         if self.collapse_coord and "percentile" in self.collapse_coord:
             raise NotImplementedError("percentile rebadging is outside the CUDA hot path")
         if self.threshold_units is not None and str(self.threshold_units) != str(input_cube.units):
@@ -210,9 +209,25 @@ class Threshold(PostProcessingPlugin):
         if masked:
             m_t = np.ascontiguousarray(np.transpose(np.ma.getmaskarray(data), perm))
             mnd = torch.from_numpy(m_t.reshape((n_collapse,) + kept_shape).astype(np.uint8)).cuda()
-        out, contrib, status = engine.threshold(dev, self._engine_thresholds(), mask_nd=mnd,
-                                                collapse_leading=True)
-        res = out.cpu().numpy()                    # (T, kept...)
+        n_vic = 0
+        if self.vicinity is not None:
+            # threshold.py:637-641, :473-518: radii in grid cells, land and sea spread separately
+            from .utilities.spatial import distance_to_number_of_grid_cells
+
+            cells = [distance_to_number_of_grid_cells(input_cube, radius) for radius in self.vicinity]
+            lm = None
+            if landmask is not None:
+                lm = torch.from_numpy(np.ascontiguousarray(np.asarray(landmask.data).astype(bool))
+                                      .astype(np.uint8)).cuda()
+            n_vic = len(cells)
+            out, contrib, status = engine.threshold_vicinity(dev, self._engine_thresholds(), cells, mask_nd=mnd,
+                                                             landmask=lm, collapse_leading=True)
+            res = out.cpu().numpy()                # (V, T, kept...)
+            res = np.moveaxis(res, 0, 1)           # (T, V, kept...)
+        else:
+            out, contrib, status = engine.threshold(dev, self._engine_thresholds(), mask_nd=mnd,
+                                                    collapse_leading=True)
+            res = out.cpu().numpy()                # (T, kept...)
         contrib = contrib.cpu().numpy()
         engine.check_status(status)
         valid = contrib.astype(bool)
@@ -220,13 +235,16 @@ class Threshold(PostProcessingPlugin):
             res = np.ma.masked_array(res, mask=np.broadcast_to(~valid, res.shape))
 
         # dimension order: time, realization, threshold, rest (threshold.py:744-753), squeezed (:731)
+        # with vicinity: ..., threshold, radius_of_vicinity, rest (:744-753)
         kept_names = [dim_names[d] for d in keep_dims]
         front = [i for i, n in enumerate(kept_names) if n in ("time", "realization")]
         front.sort(key=lambda i: ["time", "realization"].index(kept_names[i]))
         rest = [i for i in range(len(kept_names)) if i not in front]
-        axes = [i + 1 for i in front] + [0] + [i + 1 for i in rest]
+        lead = 2 if n_vic else 1                   # leading axes of `res` that are not cube dims
+        axes = [i + lead for i in front] + list(range(lead)) + [i + lead for i in rest]
         res = np.ma.transpose(res, axes) if isinstance(res, np.ma.MaskedArray) else np.transpose(res, axes)
-        out_names = [kept_names[i] for i in front] + ["__threshold__"] + [kept_names[i] for i in rest]
+        out_names = ([kept_names[i] for i in front] + ["__threshold__"] + (["__vicinity__"] if n_vic else [])
+                     + [kept_names[i] for i in rest])
         squeeze_axes = tuple(i for i, s in enumerate(res.shape) if s == 1)
         res = res.squeeze(axis=squeeze_axes) if squeeze_axes else res
 
@@ -238,10 +256,19 @@ class Threshold(PostProcessingPlugin):
             thr_coord = Coord(np.array(self.thresholds, dtype=FLOAT_DTYPE), self.threshold_coord_name,
                               str(input_cube.units), var_name="threshold",
                               attributes={"spp__relative_to_threshold": self.comparison_operator.spp_string})
+            vic_coord = None
+            if n_vic:
+                # spatial.py:1026-1060 create_vicinity_coord
+                vic_coord = Coord(np.array(self.vicinity, dtype=FLOAT_DTYPE), "radius_of_vicinity", "m")
             result._dim_coords = []
             pos = 0
             for i, name in enumerate(out_names):
-                coord = thr_coord if name == "__threshold__" else (old[name].copy() if name in old else None)
+                if name == "__threshold__":
+                    coord = thr_coord
+                elif name == "__vicinity__":
+                    coord = vic_coord
+                else:
+                    coord = old[name].copy() if name in old else None
                 if i in squeeze_axes:
                     if coord is not None:
                         result._scalar_coords.append(coord)
@@ -252,7 +279,8 @@ class Threshold(PostProcessingPlugin):
             for name in (self.collapse_coord or []):
                 if name == "realization":
                     result.remove_coord("realization")
-            result.rename("probability_of_{}_{}_threshold".format(self.threshold_coord_name, relative))
+            result.rename("probability_of_{}{}_{}_threshold".format(
+                self.threshold_coord_name, "_in_vicinity" if n_vic else "", relative))
             result.units = "1"
         return result
 

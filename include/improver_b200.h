@@ -119,6 +119,21 @@ int nbh_threshold_f32(const float* in, const uint8_t* mask_nd, float* out, int32
                       const NbhThreshold* thresholds, int32_t n_thresholds,
                       int64_t n_collapse, int64_t n_points, int32_t* status, void* stream);
 
+/* Threshold "in vicinity": replaces Threshold._vicinity_processing (improver/threshold.py:473-518)
+ * with maximum_within_vicinity (improver/utilities/spatial.py:740-855) inside the accumulation
+ * loop of Threshold.process (threshold.py:661-707).
+ *   in        float32 (n_collapse, n_planes, ny, nx); mask_nd uint8 same shape or NULL (non-zero = masked)
+ *   landmask  uint8 (ny, nx) or NULL: non-zero = land; land and sea points are spread separately
+ *   vicinity_cells  HOST array of n_vicinity radii in grid cells (square of side 2 r + 1)
+ *   out       float32 (n_vicinity, T, n_planes, ny, nx): mean over unmasked members of the
+ *             maximum truth value within the vicinity
+ *   contrib   int32 (n_planes, ny, nx) or NULL: number of unmasked members (threshold.py:679)
+ */
+int nbh_threshold_vicinity_f32(const float* in, const uint8_t* mask_nd, const uint8_t* landmask, float* out,
+                               int32_t* contrib, const NbhThreshold* thresholds, int32_t n_thresholds,
+                               const int32_t* vicinity_cells, int32_t n_vicinity, int64_t n_collapse,
+                               int64_t n_planes, int32_t ny, int32_t nx, int32_t* status, void* stream);
+
 /* Measurement aid (bench.py roofline): when enabled, the dominant kernel of
  * the next nbh_square_f32 / nbh_circular_f32 / nbh_percentiles_f32 call is
  * bracketed by CUDA events on the caller's stream.  nbh_profile_last_ms

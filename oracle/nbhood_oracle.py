@@ -25,6 +25,7 @@ from typing import Optional, Sequence, Tuple
 
 import numpy as np
 from scipy.ndimage import correlate as _correlate
+from scipy.ndimage import maximum_filter as _maximum_filter
 
 F32 = np.float32
 
@@ -114,6 +115,75 @@ def threshold_cube(data, thresholds, bounds, comparison=">", collapse_leading=Fa
     valid = contrib.astype(bool)
     for i in range(len(thresholds)):
         out[i, valid] = np.divide(out[i][valid], contrib[valid])
+    inv = None if valid.all() else ~valid
+    return out, inv, contrib
+
+
+# value the reference uses to take masked / other-surface points out of a maximum:
+# -1 * netCDF4.default_fillvals["f4"] (improver/utilities/spatial.py:851)
+VICINITY_FILL = -9.969209968386869e36
+
+
+def maximum_within_vicinity(grid, grid_point_radius: int, landmask=None):
+    """improver/utilities/spatial.py:740-855 (`operator_within_vicinity` with the
+    maximum filter): square maximum of side 2 * radius + 1, edges replicated,
+    masked points excluded, land and sea points processed separately when a
+    land mask is given.  NaN-free input (the callers raise on NaN first)."""
+    width = 2 * int(grid_point_radius) + 1
+    processed = grid.copy()
+    if np.ma.is_masked(grid):
+        unmasked_grid = grid.data.copy()
+        unmasked_grid[grid.mask] = VICINITY_FILL
+    else:
+        unmasked_grid = grid.copy()
+    if landmask is not None:
+        patch = np.empty_like(grid)
+        for match in (True, False):
+            matched = unmasked_grid.copy()
+            matched[landmask != match] = VICINITY_FILL
+            filtered = _maximum_filter(matched, size=width, mode="nearest")
+            patch = np.where(landmask == match, filtered, patch)
+    else:
+        patch = _maximum_filter(unmasked_grid, size=width, mode="nearest")
+    if np.ma.is_masked(grid):
+        processed.data[~grid.mask] = patch[~grid.mask]
+    else:
+        processed = patch
+    return processed
+
+
+def threshold_vicinity_cube(data, thresholds, bounds, comparison, vicinity_cells, landmask=None,
+                            collapse_leading=False):
+    """improver/threshold.py:643-713 with `vicinity` set (:473-518): per slice and
+    threshold the truth value is spread with `maximum_within_vicinity` (every 2-D
+    slice separately) before it is accumulated over the collapsed axis.
+
+    data: float32 (S, ..., y, x) when collapse_leading else (..., y, x).  Returns
+    (values float32 (V, T, ..., y, x), invalid-mask bool or None, counts)."""
+    slices = list(data) if collapse_leading else [data]
+    shape = slices[0].shape
+    out = np.zeros((len(vicinity_cells), len(thresholds)) + shape, dtype=F32)
+    contrib = np.zeros(shape, dtype=int)
+    lm = None if landmask is None else np.asarray(landmask).astype(bool)
+    for sl in slices:
+        if np.isnan(np.ma.getdata(sl)[~np.ma.getmaskarray(sl)]).any():
+            raise ValueError("Error: NaN detected in input cube data")
+        unmasked = ~sl.mask if np.ma.is_masked(sl) else np.ones(shape, dtype=bool)
+        contrib += unmasked
+        for i, (thr, bnd) in enumerate(zip(thresholds, bounds)):
+            tv = truth_value(sl, thr, bnd, comparison)
+            for iv, cells in enumerate(vicinity_cells):
+                if tv.ndim > 2:
+                    maxes = np.zeros(tv.shape, dtype=F32)
+                    for idx in np.ndindex(*tv.shape[:-2]):
+                        maxes[idx] = maximum_within_vicinity(tv[idx], cells, lm)
+                else:
+                    maxes = maximum_within_vicinity(tv, cells, lm)
+                out[iv][i][unmasked] += np.ma.getdata(maxes)[unmasked]
+    valid = contrib.astype(bool)
+    for iv in range(len(vicinity_cells)):
+        for i in range(len(thresholds)):
+            out[iv, i, valid] = np.divide(out[iv, i][valid], contrib[valid])
     inv = None if valid.all() else ~valid
     return out, inv, contrib
 
