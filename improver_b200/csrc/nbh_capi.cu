@@ -163,7 +163,7 @@ size_t percentiles_workspace_bytes(long long, int, int, int);
 int run_threshold_vicinity(const float* in, const uint8_t* mask_nd, const uint8_t* landmask, float* out,
                            int32_t* contrib, const NbhThreshold* thresholds, int n_thresholds,
                            const int32_t* vicinity_cells, int n_vicinity, long long n_collapse,
-                           long long n_planes, int ny, int nx, int32_t* status, cudaStream_t st);
+                           long long n_planes, int ny, int nx, int32_t* status, cudaStream_t st, int raw_op = -1);
 int run_threshold(const float*, const uint8_t*, float*, int32_t*, const NbhThreshold*, int, long long,
                   long long, int32_t*, cudaStream_t);
 
@@ -245,6 +245,14 @@ int nbh_threshold_vicinity_f32(const float* in, const uint8_t* mask_nd, const ui
   return nbh::run_threshold_vicinity(in, mask_nd, landmask, out, contrib, thresholds, n_thresholds,
                                      vicinity_cells, n_vicinity, n_collapse, n_planes, ny, nx, status,
                                      static_cast<cudaStream_t>(stream));
+}
+
+int nbh_vicinity_f32(const float* in, const uint8_t* mask_nd, const uint8_t* landmask, float* out,
+                     const int32_t* vicinity_cells, int32_t n_vicinity, int32_t op, int64_t n_planes,
+                     int32_t ny, int32_t nx, int32_t* status, void* stream) {
+  NBH_REQUIRE(op == 0 || op == 1, "op must be 0 (maximum) or 1 (minimum)");
+  return nbh::run_threshold_vicinity(in, mask_nd, landmask, out, nullptr, nullptr, 0, vicinity_cells, n_vicinity,
+                                     1, n_planes, ny, nx, status, static_cast<cudaStream_t>(stream), op);
 }
 
 }  // extern "C"

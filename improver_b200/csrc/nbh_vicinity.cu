@@ -201,9 +201,12 @@ static int launch_vic(const VicParams& p, long long blocks, size_t smem, cudaStr
 int run_threshold_vicinity(const float* in, const uint8_t* mask_nd, const uint8_t* landmask, float* out,
                            int32_t* contrib, const NbhThreshold* thresholds, int n_thresholds,
                            const int32_t* vicinity_cells, int n_vicinity, long long n_collapse,
-                           long long n_planes, int ny, int nx, int32_t* status, cudaStream_t st) {
-  NBH_REQUIRE(in && out && status && thresholds && vicinity_cells, "null pointer argument");
-  NBH_REQUIRE(n_thresholds >= 1 && n_vicinity >= 1, "at least one threshold and one vicinity radius are needed");
+                           long long n_planes, int ny, int nx, int32_t* status, cudaStream_t st, int raw_op) {
+  // raw_op: -1 thresholded; 0 / 1: maximum / minimum of the data itself (no thresholds)
+  NBH_REQUIRE(in && out && status && vicinity_cells, "null pointer argument");
+  NBH_REQUIRE(raw_op >= 0 || (thresholds && n_thresholds >= 1), "at least one threshold is needed");
+  NBH_REQUIRE(n_vicinity >= 1, "at least one vicinity radius is needed");
+  if (raw_op >= 0) n_thresholds = 1;
   NBH_REQUIRE(n_collapse >= 1 && n_planes >= 1 && ny >= 1 && nx >= 1, "empty input");
   int vmax = 0;
   for (int i = 0; i < n_vicinity; ++i) {
@@ -222,15 +225,17 @@ int run_threshold_vicinity(const float* in, const uint8_t* mask_nd, const uint8_
   int t0 = 0;
   while (t0 < n_thresholds) {
     ThrDev first;
-    if (make_thr_dev(thresholds[t0], &first, mask_nd != nullptr)) return 1;
-    const bool eq = first.op == NBH_OP_EQ;
-    const bool less = first.op == NBH_OP_LT || first.op == NBH_OP_LE;
+    memset(&first, 0, sizeof(first));
+    if (raw_op < 0 && make_thr_dev(thresholds[t0], &first, mask_nd != nullptr)) return 1;
+    const bool eq = raw_op < 0 && first.op == NBH_OP_EQ;
+    const bool less = raw_op < 0 ? (first.op == NBH_OP_LT || first.op == NBH_OP_LE) : raw_op == 1;
     int v0 = 0;
     int n_t = 0;
     VicParams p;
     memset(&p, 0, sizeof(p));
     const int max_t = eq ? 1 : max(1, kVicMaxOut / min(n_vicinity, kVicMaxOut));
-    for (int i = t0; i < n_thresholds && n_t < max_t; ++i) {
+    if (raw_op >= 0) p.thr.t[n_t++] = first;
+    for (int i = t0; raw_op < 0 && i < n_thresholds && n_t < max_t; ++i) {
       ThrDev d;
       if (make_thr_dev(thresholds[i], &d, mask_nd != nullptr)) return 1;
       const bool eq_i = d.op == NBH_OP_EQ, less_i = d.op == NBH_OP_LT || d.op == NBH_OP_LE;
@@ -252,6 +257,7 @@ int run_threshold_vicinity(const float* in, const uint8_t* mask_nd, const uint8_
       p.sign = less ? -1.f : 1.f;
       int rc;
       switch (first.mode) {
+        case 0: rc = launch_vic<0>(p, blocks, smem, st); break;
         case 1: rc = launch_vic<1>(p, blocks, smem, st); break;
         case 2: rc = launch_vic<2>(p, blocks, smem, st); break;
         default: rc = launch_vic<3>(p, blocks, smem, st); break;

@@ -270,6 +270,35 @@ def threshold_vicinity(data: torch.Tensor, thresholds, vicinity_cells: Sequence[
     return out, contrib, status
 
 
+def extreme_within_vicinity(data: torch.Tensor, vicinity_cells: Sequence[int], operator: str = "max",
+                            mask_nd: Optional[torch.Tensor] = None, landmask: Optional[torch.Tensor] = None):
+    """maximum_within_vicinity / minimum_within_vicinity (spatial.py:805-903) of every 2-D
+    slice.  data float32 CUDA (..., ny, nx) -> (V, ..., ny, nx); masked points hold 0."""
+    lib = _lib.load()
+    _require_cuda(data, "data")
+    if data.dtype != torch.float32 or data.dim() < 2:
+        raise TypeError("data must be float32 with (y, x) axes")
+    if operator not in ("max", "min"):
+        raise ValueError("operator must be 'max' or 'min'")
+    data = data.contiguous()
+    ny, nx = int(data.shape[-2]), int(data.shape[-1])
+    n_planes = int(np.prod(data.shape[:-2])) if data.dim() > 2 else 1
+    cells = np.asarray([int(c) for c in vicinity_cells], dtype=np.int32)
+    out = torch.empty((len(cells),) + tuple(data.shape), dtype=torch.float32, device=data.device)
+    status = torch.zeros(2, dtype=torch.int32, device=data.device)
+    if mask_nd is not None:
+        mask_nd = (mask_nd != 0).to(torch.uint8).contiguous()
+    if landmask is not None:
+        landmask = (landmask != 0).to(torch.uint8).contiguous()
+    with torch.cuda.device(data.device):
+        _lib.check(lib.nbh_vicinity_f32(
+            data.data_ptr(), mask_nd.data_ptr() if mask_nd is not None else None,
+            landmask.data_ptr() if landmask is not None else None, out.data_ptr(),
+            cells.ctypes.data_as(C.POINTER(C.c_int32)), len(cells), 0 if operator == "max" else 1,
+            n_planes, ny, nx, status.data_ptr(), _stream_ptr()))
+    return out, status
+
+
 def neighbourhood_percentiles(data: torch.Tensor, cells: int, percentiles: Sequence[float]):
     """Percentiles of the circular neighbourhood of every point
     (nbhood.py:649-667).  data float32 (..., ny, nx) -> (..., P, ny, nx)."""

@@ -134,6 +134,15 @@ int nbh_threshold_vicinity_f32(const float* in, const uint8_t* mask_nd, const ui
                                const int32_t* vicinity_cells, int32_t n_vicinity, int64_t n_collapse,
                                int64_t n_planes, int32_t ny, int32_t nx, int32_t* status, void* stream);
 
+/* Maximum / minimum within a square vicinity of every point of every 2-D slice: replaces
+ * maximum_within_vicinity / minimum_within_vicinity (improver/utilities/spatial.py:805-903) as used by
+ * OccurrenceWithinVicinity.process (:1176-1255).  op: 0 maximum, 1 minimum.
+ *   in float32 (n_planes, ny, nx) -> out float32 (n_vicinity, n_planes, ny, nx); masked points
+ *   (mask_nd) neither contribute nor are written (0 is stored there). */
+int nbh_vicinity_f32(const float* in, const uint8_t* mask_nd, const uint8_t* landmask, float* out,
+                     const int32_t* vicinity_cells, int32_t n_vicinity, int32_t op, int64_t n_planes,
+                     int32_t ny, int32_t nx, int32_t* status, void* stream);
+
 /* Measurement aid (bench.py roofline): when enabled, the dominant kernel of
  * the next nbh_square_f32 / nbh_circular_f32 / nbh_percentiles_f32 call is
  * bracketed by CUDA events on the caller's stream.  nbh_profile_last_ms

@@ -175,3 +175,45 @@ def test_plugin_vicinity_collapse_and_errors():
     assert not result.coords("realization")
     with pytest.raises(ValueError, match="Cannot apply land-mask cube without in-vicinity processing"):
         Threshold(threshold_values=0.5)(cube, lm)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("operator", ["max", "min"])
+def test_occurrence_within_vicinity_vs_reference_semantics(operator):
+    """OccurrenceWithinVicinity (spatial.py:1077-1255) for the max / min operators: oracle
+    (operator_within_vicinity restated with scipy's maximum_filter) on every 2-D slice,
+    land / sea separation, masked points kept and re-masked, radius axis after the leading dims."""
+    from improver_b200.synthetic_data import set_up_variable_cube
+    from improver_b200.utilities.spatial import OccurrenceWithinVicinity
+
+    rng = np.random.default_rng(12)
+    data = rng.random((3, 21, 34)).astype(np.float32)
+    land = (rng.random((21, 34)) < 0.4)
+    lm = set_up_variable_cube(land.astype(np.float32), name="land_binary_mask", units="1")
+    sign = 1.0 if operator == "max" else -1.0
+    for masked in (False, True):
+        inp = np.ma.masked_array(data, rng.random(data.shape) < 0.15) if masked else data
+        cube = set_up_variable_cube(inp, name="lwe_precipitation_rate", units="m s-1")
+        result = OccurrenceWithinVicinity(grid_point_radii=[1, 3], land_mask_cube=lm, operator=operator)(cube)
+        assert result.shape == (3, 2, 21, 34)
+        assert result.name() == "lwe_precipitation_rate_in_vicinity"
+        for iv, cells in enumerate((1, 3)):
+            for k in range(3):
+                sl = inp[k]
+                neg = sign * sl if not masked else np.ma.masked_array(sign * sl.data, sl.mask)
+                exp = sign * np.ma.getdata(orc.maximum_within_vicinity(neg, cells, land))
+                got = result.data[k, iv]
+                if masked:
+                    np.testing.assert_array_equal(np.ma.getmaskarray(got), sl.mask)
+                    np.testing.assert_array_equal(np.ma.getdata(got)[~sl.mask], exp[~sl.mask])
+                    np.testing.assert_array_equal(np.ma.getdata(got)[sl.mask], sl.data[sl.mask])
+                else:
+                    np.testing.assert_array_equal(got, exp)
+    single = OccurrenceWithinVicinity(radii=[4000.0])(set_up_variable_cube(data[0], name="probability_of_rain_above_threshold", units="1"))
+    assert single.shape == (21, 34)
+    assert single.name() == "probability_of_rain_in_vicinity_above_threshold"
+    np.testing.assert_array_equal(single.data, orc.maximum_within_vicinity(data[0], 2))
+    with pytest.raises(ValueError, match="only one of radii"):
+        OccurrenceWithinVicinity(radii=[2000], grid_point_radii=[1])
+    with pytest.raises(ValueError, match="non-zero value"):
+        OccurrenceWithinVicinity()
