@@ -182,7 +182,8 @@ def run_ours(args):
     # synthetic gamma(2, 1.5) cube generated on the device (sum of two exponentials)
     gen = torch.Generator(device=dev)
     gen.manual_seed(3 + rank)
-    cube = torch.empty((R, L, NY, NX), dtype=torch.float32, device=dev)
+    # device layout: members 64 KiB further apart than the contiguous stride (pipeline.member_padded_empty)
+    cube = pipeline.member_padded_empty((R, L, NY, NX), dev)
     for r in range(R):
         u = torch.rand((2, L, NY, NX), generator=gen, device=dev).clamp_min_(1e-12)
         cube[r] = -1.5 * (torch.log(u[0]) + torch.log(u[1]))
@@ -233,7 +234,7 @@ def run_ours(args):
     e2e_steps = max(1, min(args.steps, 3))
     e2e_value = None
     if not args.no_e2e:
-        host_in = pipeline.pinned_like(cube)            # pinned host copy of this rank's cube
+        host_in = torch.empty((R, L, NY, NX), dtype=torch.float32, pin_memory=True)   # contiguous pinned host cube
         host_in.copy_(cube)
         torch.cuda.synchronize()
         host_out = pipeline.threshold_neighbourhood_mean_host(
@@ -262,7 +263,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "shape": [R, L, NY, NX], "cells": CELLS,
                        "thresholds": T, "l2": "inputs (2.6 GB/step) larger than L2; no flush needed",
-                       "sharding": "one full cube per GPU, lead-time slices independent, no collective"},
+                       "sharding": "one full cube per GPU, lead-time slices independent, no collective",
+                       "device_layout": "(R, L, y, x) float32, member stride padded by 64 KiB"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,

@@ -92,7 +92,12 @@ def neighbourhood(
         raise TypeError("data must be float32")
     if data.dim() < 2:
         raise ValueError("data must have at least two dimensions (y, x)")
-    data = data.contiguous()
+    # a member axis with a padded stride is taken as it is (every member block contiguous):
+    # the device layout of a fused cube is free, see pipeline.member_padded_empty
+    padded_members = (collapse_members and data.dim() >= 3 and not data.is_contiguous()
+                      and data[0].is_contiguous() and data.stride(0) >= data[0].numel())
+    if not padded_members:
+        data = data.contiguous()
     ny, nx = int(data.shape[-2]), int(data.shape[-1])
     lead = tuple(int(s) for s in data.shape[:-2])
     if collapse_members:
@@ -103,7 +108,7 @@ def neighbourhood(
         n_members, plane_shape = 1, lead
     n_planes = int(np.prod(plane_shape)) if plane_shape else 1
     slice_elems = ny * nx
-    member_stride = n_planes * slice_elems if collapse_members else 0
+    member_stride = (int(data.stride(0)) if padded_members else n_planes * slice_elems) if collapse_members else 0
     if n_planes == 0 or slice_elems == 0:
         raise ValueError("empty input")
 

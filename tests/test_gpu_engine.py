@@ -351,3 +351,22 @@ def test_row_stream_rows_kernel_matches_oracle(shape, cells, wrap, monkeypatch):
         engine.check_status(status)
         exp = orc.threshold_square_mean(gam, [2.0], [(1.4, 2.6)], ">", cells)
         _assert_close(out.cpu().numpy()[:, 0], exp[:, 0])
+
+
+def test_member_padded_device_layout_is_equivalent():
+    """A fused cube whose member blocks are padded apart (pipeline.member_padded_empty, the layout
+    bench.py and the host pipeline use) gives bit-identical results to the contiguous cube."""
+    from improver_b200 import engine, pipeline
+
+    rng = np.random.default_rng(51)
+    data = rng.gamma(2.0, 1.5, (6, 3, 70, 130)).astype(np.float32)
+    cube = pipeline.member_padded_empty(data.shape, "cuda", pad_bytes=4096)
+    assert not cube.is_contiguous() and cube[0].is_contiguous()
+    cube.copy_(torch.from_numpy(data))
+    thr = [(2.0, 1.4, 2.6, ">")]
+    a, _, st = engine.neighbourhood(cube, 4, thresholds=thr, collapse_members=True)
+    engine.check_status(st)
+    b, _, st = engine.neighbourhood(_dev(data), 4, thresholds=thr, collapse_members=True)
+    engine.check_status(st)
+    np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
+    _assert_close(a.cpu().numpy(), orc.threshold_square_mean(data, [2.0], [(1.4, 2.6)], ">", 4))
