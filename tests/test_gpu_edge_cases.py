@@ -164,3 +164,18 @@ def test_circular_wrap_x_extension(cells):
         pm = np.pad(m, ((0, 0), (cells, cells)), mode="wrap") if m is not None else None
         exp, _ = orc.neighbourhood_cube(padded, pm, method="circular", cells=cells)
         _close(out.cpu().numpy(), exp[..., cells:-cells])
+
+
+@pytest.mark.parametrize("shape,cells", [((2, 1, 4, 6), 1), ((11, 2, 9, 64), 4), ((64, 1, 24, 40), 2),
+                                         ((3, 7, 5, 1042), 5), ((13, 1, 300, 66), 3), ((2, 150, 12, 34), 2)])
+def test_row_stream_kernel_odd_shapes(shape, cells):
+    """Row-streaming fused kernel on awkward shapes: grids smaller than the neighbourhood, prime
+    member counts (one member per stage), 64 members, more planes than SMs, single-window rows."""
+    from improver_b200 import engine
+
+    rng = np.random.default_rng(61)
+    data = rng.gamma(2.0, 1.5, shape).astype(np.float32)
+    exp = orc.threshold_square_mean(data, [2.0], [(1.4, 2.6)], ">", cells)
+    out, _, st = engine.neighbourhood(_dev(data), cells, thresholds=[(2.0, 1.4, 2.6, ">")], collapse_members=True)
+    engine.check_status(st)
+    np.testing.assert_allclose(out.cpu().numpy(), exp, atol=1e-5)
