@@ -9,7 +9,7 @@ int env_int(const char* name, int dflt);
 // Requirements: fused member path (n_members >= 2), no periodic x, even nx and
 // 8-byte aligned rows (float2 reads of the staged rows), member stride a multiple
 // of four floats (one alignment shift per row), the whole row covered by at most
-// kRsMaxWindows 64-column windows, and at least two stages of shared memory.
+// kRsMaxWindows 64-column windows per x panel, and at least two stages of shared memory.
 bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid) {
   if (!env_int("NBH_SQ_RS", 1)) return false;
   const int r = d.cells, nb = 2 * r + 1, R = d.n_members;
@@ -20,13 +20,16 @@ bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid) {
   const int W = (64 - hl - r) & ~1;
   const int W0 = (64 - r) & ~1;
   if (W < 32) return false;
-  const int n_windows = 1 + (d.nx > W0 ? (d.nx - W0 + W - 1) / W : 0);
-  if (n_windows > kRsMaxWindows) return false;
+  // rows wider than kRsMaxWindows windows are split into x panels of equal window count
+  const int n_windows_total = 1 + (d.nx > W0 ? (d.nx - W0 + W - 1) / W : 0);
+  const int n_panels = (n_windows_total + kRsMaxWindows - 1) / kRsMaxWindows;
+  const int n_windows = (n_windows_total + n_panels - 1) / n_panels;
   int dev = 0, smem_max = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (smem_max <= 0) smem_max = 227 * 1024;
-  const int pitch = (d.nx + 3 + 3) / 4 * 4;            // up to 3 floats of alignment shift
+  const int seg_cols = min(d.nx, n_windows * W + hl + r + (W0 - W));    // widest staged segment
+  const int pitch = (seg_cols + 3 + 3) / 4 * 4;        // up to 3 floats of alignment shift
   const size_t fixed = sq_rs_fixed_smem(nb, n_windows) + 256;
   if (fixed + 2 * (size_t)pitch * 4 > (size_t)smem_max) return false;
   const size_t avail = (size_t)smem_max - fixed;
@@ -40,7 +43,8 @@ bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid) {
   int n_stages = (int)min((size_t)kRsMaxStages, avail / ((size_t)ms * pitch * 4));
   n_stages = min(n_stages, env_int("NBH_SQ_RS_STAGES", kRsMaxStages));
   if (n_stages < 2) return false;
-  g->n_windows = n_windows; g->W0 = W0; g->W = W; g->hl = hl;
+  g->n_windows = n_windows; g->n_panels = n_panels; g->n_windows_total = n_windows_total;
+  g->W0 = W0; g->W = W; g->hl = hl;
   g->ms = ms; g->n_stages = n_stages; g->pitch = pitch;
   // fixed-point scale: nb^2 * R * 2^shift < 2^31 (window sums are exact modulo 2^32)
   int shift = 0;
@@ -48,7 +52,7 @@ bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid) {
   if (d.n_thresholds > 0 && shift < 12) return false;   // huge windows: keep the float64 kernels
   g->fx_shift = shift;
   g->wait_ns = (unsigned)env_int("NBH_SQ_RS_WAIT_NS", 1000);
-  g->rows_total = d.n_planes * (long long)max(d.n_thresholds, 1) * d.ny;
+  g->rows_total = d.n_planes * (long long)max(d.n_thresholds, 1) * n_panels * d.ny;
   // one block per SM; every share at least ~4r rows so the y halo stays a minor cost
   const long long min_share = max(16, 4 * r);
   long long blocks = min((long long)sm_count(), max(1LL, g->rows_total / min_share));

@@ -41,7 +41,9 @@ constexpr int kRsThreads = (kRsMaxWindows + kRsProducers) * 32;
 constexpr int kRsMaxStages = 16;
 
 struct SqRsGeom {
-  int n_windows;        // consumer warps = 64-column windows per row
+  int n_windows;        // consumer warps = 64-column windows per x panel
+  int n_panels;         // x panels per row (rows wider than kRsMaxWindows windows are split)
+  int n_windows_total;  // windows per full row
   int W0, W, hl;        // output columns of window 0 / the others, left halo (even, >= r)
   int ms;               // items (member rows) per stage; divides n_members
   int n_stages;
@@ -144,17 +146,24 @@ square_rs_kernel(const __grid_constant__ SqParams p, const SqRsGeom g) {
     unsigned round = 0;
     RsPieces pieces(g.share, g.rows_total, p.ny, blockIdx.x);
     long long unit; int ya, yb;
-    while (pieces.next(&unit, &ya, &yb)) {
+    long long task;
+    while (pieces.next(&task, &ya, &yb)) {
+      unit = task / g.n_panels;
+      const int panel = (int)(task - unit * g.n_panels);
       const long long plane = unit / p.n_thr;
       const int dir = pieces.dir;
       const int y_lo = max(ya - r, 0), y_hi = min(yb - 1 + r, p.ny - 1);
       const int n_in = y_hi - y_lo + 1;
-      const float* plane_ptr = p.in + plane * p.plane_stride;
+      // columns of this panel: from the first window's load start to the last window's right halo
+      const int gw0 = panel * NW, gw1 = min(gw0 + NW, g.n_windows_total) - 1;
+      const int seg0 = gw0 == 0 ? 0 : g.W0 + (gw0 - 1) * g.W - g.hl;
+      const int seg1 = min(p.nx, (gw1 == 0 ? 0 : g.W0 + (gw1 - 1) * g.W) + (gw1 == 0 ? g.W0 : g.W) + r);
+      const float* plane_ptr = p.in + plane * p.plane_stride + seg0;
       for (int k = 0; k < n_in; ++k) {
         const int y = dir > 0 ? y_lo + k : y_hi - k;
         const float* row = plane_ptr + (long long)y * p.nx;
         const unsigned shift_b = (unsigned)(reinterpret_cast<unsigned long long>(row) & 15ull);
-        const unsigned bytes = (shift_b + (unsigned)p.nx * 4u + 15u) & ~15u;
+        const unsigned bytes = (shift_b + (unsigned)(seg1 - seg0) * 4u + 15u) & ~15u;
         const char* src = reinterpret_cast<const char*>(row) - shift_b;
         for (int m0 = 0; m0 < R; m0 += MS) {
           mbar_wait_hint(empty0 + 8 * s, (round & 1u) ^ 1u, g.wait_ns);
@@ -189,51 +198,58 @@ square_rs_kernel(const __grid_constant__ SqParams p, const SqRsGeom g) {
   unsigned* ring_u = reinterpret_cast<unsigned*>(ring);
 
   const bool sum_only = (p.flags & NBH_SUM_ONLY) != 0;
-  // window geometry: window 0 starts at the domain edge and needs no left halo
-  const int x0 = warp == 0 ? 0 : g.W0 + (warp - 1) * g.W;
-  const int load0 = warp == 0 ? 0 : x0 - g.hl;
-  const int wk = warp == 0 ? g.W0 : g.W;
-  const int c_out0 = x0 - load0;
   const int c0 = lane * VEC;
-  const int gxr = load0 + c0;
-  const bool col_active = gxr < p.nx;
-  const int gx = col_active ? gxr : 0;             // inactive lanes read column 0 (discarded)
-  const bool band_l = !sum_only && col_active && (gxr + VEC - 1 <= r);
-  const bool band_r = !sum_only && col_active && (gxr >= p.nx - 1 - r);
-  const bool warp_band_l = __any_sync(0xffffffffu, band_l), warp_band_r = __any_sync(0xffffffffu, band_r);
-  const bool is_out = (c0 >= c_out0) && (c0 < c_out0 + wk) && col_active;
   const unsigned long long all_members = R >= 64 ? ~0ull : ((1ull << R) - 1ull);
   const float fx_scale = FX ? (float)(1u << g.fx_shift) : 1.f;
   const double fx_inv = FX ? 1.0 / (double)(1u << g.fx_shift) : 1.0;
-
-  // lane-constant pieces of the output stage
-  int idx_hi[VEC], idx_lo[VEC];
-  double rcol[VEC];
-#pragma unroll
-  for (int v = 0; v < VEC; ++v) {
-    const int cc = c0 + v;
-    idx_hi[v] = cc + r + 1;
-    idx_lo[v] = max(cc - r, 0);
-    const int xo = gx + v;
-    const int cols_in = min(xo + r, p.nx - 1) - max(xo - r, 0) + 1;
-    rcol[v] = (sum_only ? 1.0 : rtab[min(max(cols_in, 1), nb)] * p.inv_members) * fx_inv;
-  }
   const double inv_members_fx = p.inv_members * fx_inv;
   if (lane == 0) { hrow[0] = 0.0; }                 // also zeroes hrow_u[0]
+  int idx_hi[VEC], idx_lo[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    idx_hi[v] = c0 + v + r + 1;
+    idx_lo[v] = max(c0 + v - r, 0);
+  }
 
   const unsigned pitch_b = (unsigned)g.pitch * 4u;
-  const unsigned stage_lane0 = smem_u32(stages) + (unsigned)gx * 4u;    // this lane's column in stage 0
+  const unsigned stages_u32 = smem_u32(stages);
   float nanacc = 0.f;
-  // stage cursor: barrier address, this lane's address in the stage, phase parity
+  // stage cursor: barrier address, stage address, phase parity
   int s = 0;
-  unsigned parity = 0, bar = full0, st_addr = stage_lane0;
+  unsigned parity = 0, bar = full0, st_addr = stages_u32;
   auto next_stage = [&]() {
     bar += 8; st_addr += stage_bytes;
-    if (++s == NS) { s = 0; parity ^= 1u; bar = full0; st_addr = stage_lane0; }
+    if (++s == NS) { s = 0; parity ^= 1u; bar = full0; st_addr = stages_u32; }
   };
   RsPieces pieces(g.share, g.rows_total, p.ny, blockIdx.x);
-  long long unit; int ya, yb;
-  while (pieces.next(&unit, &ya, &yb)) {
+  long long task, unit; int ya, yb;
+  while (pieces.next(&task, &ya, &yb)) {
+    unit = task / g.n_panels;
+    const int panel = (int)(task - unit * g.n_panels);
+    // ---- window geometry of this piece (lane constants): window 0 of the row starts at the
+    // domain edge and needs no left halo; windows past the end of the row are idle ----
+    const int gw = panel * NW + warp;                  // window index within the full row
+    const int gw0 = panel * NW;
+    const int seg0 = gw0 == 0 ? 0 : g.W0 + (gw0 - 1) * g.W - g.hl;     // first staged column
+    const int x0 = gw == 0 ? 0 : g.W0 + (gw - 1) * g.W;
+    const int load0 = gw == 0 ? 0 : x0 - g.hl;
+    const int wk = gw == 0 ? g.W0 : g.W;
+    const int c_out0 = x0 - load0;
+    const int gxr = load0 + c0;
+    const bool col_active = gw < g.n_windows_total && gxr < p.nx;
+    const int gx = col_active ? gxr : seg0;            // inactive lanes read the first staged column (discarded)
+    const bool band_l = !sum_only && col_active && (gxr + VEC - 1 <= r);
+    const bool band_r = !sum_only && col_active && (gxr >= p.nx - 1 - r);
+    const bool warp_band_l = __any_sync(0xffffffffu, band_l), warp_band_r = __any_sync(0xffffffffu, band_r);
+    const bool is_out = (c0 >= c_out0) && (c0 < c_out0 + wk) && col_active;
+    double rcol[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int xo = gx + v;
+      const int cols_in = min(xo + r, p.nx - 1) - max(xo - r, 0) + 1;
+      rcol[v] = (sum_only ? 1.0 : rtab[min(max(cols_in, 1), nb)] * p.inv_members) * fx_inv;
+    }
+    const unsigned lane_col_b = (unsigned)(gx - seg0) * 4u;            // this lane's byte offset in a staged row
     const long long plane = unit / p.n_thr;
     const int t = (int)(unit - plane * p.n_thr);
     const ThrDev& thr = p.thr.t[TM ? t : 0];
@@ -241,7 +257,7 @@ square_rs_kernel(const __grid_constant__ SqParams p, const SqRsGeom g) {
     const int n_rows = (yb - ya) + 2 * r;
     const int y_first = dir > 0 ? ya - r : yb - 1 + r;
     const long long obase0 = unit * (long long)p.ny * p.nx;
-    const unsigned long long plane_elem0 = in_elem0 + (unsigned long long)(plane * p.plane_stride);
+    const unsigned long long plane_elem0 = in_elem0 + (unsigned long long)(plane * p.plane_stride) + (unsigned long long)seg0;
 
     for (int q = 0; q < nb; ++q) *reinterpret_cast<float2*>(ring + q * WS + c0) = make_float2(0.f, 0.f);
     double V0 = 0.0, V1 = 0.0;
@@ -272,7 +288,7 @@ square_rs_kernel(const __grid_constant__ SqParams p, const SqRsGeom g) {
         if (!flagged) {
           for (int m0 = 0; m0 < R; m0 += MS) {
             mbar_wait_hint(bar, parity, g.wait_ns);
-            unsigned q = st_addr + shift_b;
+            unsigned q = st_addr + lane_col_b + shift_b;
 #pragma unroll 3
             for (int j = 0; j < MS; ++j) {
               const float2 d = lds_f2(q);
@@ -291,7 +307,7 @@ square_rs_kernel(const __grid_constant__ SqParams p, const SqRsGeom g) {
           unsigned long long ne = 0;
           for (int m0 = 0; m0 < R; m0 += MS) {
             mbar_wait_hint(bar, parity, g.wait_ns);
-            unsigned q = st_addr + shift_b;
+            unsigned q = st_addr + lane_col_b + shift_b;
             unsigned long long bit = 1ull << m0;
 #pragma unroll 2
             for (int j = 0; j < MS; ++j) {

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from improver_b200 import engine, pipeline
 
-R, L, NY, NX = 18, 36, 970, 1042
+R, L, NY, NX = (int(v) for v in os.environ.get("SWEEP_SHAPE", "18,36,970,1042").split(","))
 dev = torch.device("cuda", 0)
 thr = [(2.0, 1.4, 2.6, ">")]
 out = torch.empty((L, 1, NY, NX), dtype=torch.float32, device=dev)

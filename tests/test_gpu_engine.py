@@ -259,12 +259,13 @@ def test_multi_threshold_variant_matches_oracle(monkeypatch):
 
 
 @pytest.mark.parametrize("shape,cells", [((6, 3, 97, 130), 5), ((18, 2, 64, 1042), 5), ((7, 4, 33, 58), 2),
-                                         ((4, 5, 120, 64), 1), ((12, 2, 51, 700), 9)])
+                                         ((4, 5, 120, 64), 1), ((12, 2, 51, 700), 9),
+                                         ((4, 2, 30, 1100), 3), ((3, 2, 20, 2560), 5)])
 def test_row_stream_kernel_matches_oracle_and_warp_kernel(shape, cells, monkeypatch):
     """Row-streaming fused square kernel (bulk-copy staged full rows, default for
     the fused member path): oracle parity with and without an external mask, several
     thresholds, an all-ones member with an edge blob (trimming fix-up flags), shares
-    that straddle planes, and equality with the warp kernel it replaces (NBH_SQ_RS=0)."""
+    that straddle planes, rows split into x panels (nx > 20 windows), and equality with the warp kernel it replaces (NBH_SQ_RS=0)."""
     from improver_b200 import engine
 
     rng = np.random.default_rng(41)
