@@ -138,7 +138,7 @@ class NeighbourhoodProcessing(BaseNeighbourhoodProcessing):
         from .. import engine
 
         if np.iscomplexobj(data):
-            raise NotImplementedError("complex (degrees_as_complex) input is outside the CUDA hot path")
+            return self._calculate_neighbourhood_complex(data, mask)
         cells = self._cells()
         weighted = self.weighted_mode
         if self.neighbourhood_method == "circular" and hasattr(self, "kernel"):
@@ -163,6 +163,39 @@ class NeighbourhoodProcessing(BaseNeighbourhoodProcessing):
             weighted_mode=weighted, sum_only=self.sum_only, want_mask=self.re_mask)
         res = out.cpu().numpy()
         engine.check_status(status)
+        if self.re_mask:
+            res = np.ma.masked_array(res, omask.cpu().numpy().astype(bool), copy=False)
+        return res
+
+    def _calculate_neighbourhood_complex(self, data, mask=None):
+        """Complex input (wind directions as unit vectors, nbhood.py:277-280): the neighbourhood
+        sum is linear, so the real part, the imaginary part and the valid-point count are three
+        `sum_only` launches of the float kernels and the mean is their quotient.  The reference
+        never trims complex data against ones (nbhood.py:355-357), so no fix-up applies; its
+        lexicographic clip to [nanmin, nanmax] is restated with numpy."""
+        from .. import engine
+
+        cells = self._cells()
+        in_mask = np.ma.getmaskarray(data) if isinstance(data, np.ma.MaskedArray) else None
+        raw = np.asarray(np.ma.getdata(data))
+        m2 = _to_device((np.asarray(mask) != 0).astype(np.uint8)) if mask is not None else None
+        mnd = _to_device(in_mask.astype(np.uint8)) if in_mask is not None else None
+        parts = []
+        for comp in (raw.real, raw.imag, np.ones(raw.shape, np.float32)):
+            out, omask, status = engine.neighbourhood(
+                _to_device(np.ascontiguousarray(comp, dtype=np.float32)), cells, method=self.neighbourhood_method,
+                mask2d=m2, mask_nd=mnd, weighted_mode=self.weighted_mode, sum_only=True, want_mask=True)
+            parts.append(out.cpu().numpy().astype(np.float64))
+            engine.check_status(status)
+        res = parts[0] + 1j * parts[1]
+        if not self.sum_only:
+            valid = raw if in_mask is None else raw[~in_mask]
+            min_val, max_val = np.nanmin(valid), np.nanmax(valid)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                res = res / parts[2]
+            res[parts[2] == 0] = np.nan
+            res = res.clip(min_val, max_val)
+        res = res.astype(np.complex64)
         if self.re_mask:
             res = np.ma.masked_array(res, omask.cpu().numpy().astype(bool), copy=False)
         return res
@@ -322,10 +355,11 @@ class MetaNeighbourhood(BasePlugin):
                 raise RuntimeError("Cannot process complex numbers with circular neighbourhoods")
 
     def process(self, cube, mask=None):
+        """nbhood.py:852-894."""
         if self._degrees_as_complex:
-            raise NotImplementedError("degrees_as_complex is outside the CUDA hot path (SURVEY.md §8f)")
-        if self._halo_radius is not None:
-            raise NotImplementedError("halo_radius removal is outside the CUDA hot path (SURVEY.md §8f)")
+            # improver/utilities/complex_conversion.py:10-36 (deg_to_complex, radius 1)
+            angle_rad = np.deg2rad(cube.data)
+            cube = cube.copy(data=np.cos(angle_rad) + 1j * np.sin(angle_rad))
         if self._neighbourhood_output == "probabilities":
             result = NeighbourhoodProcessing(
                 self._neighbourhood_shape, self._radius_or_radii, lead_times=self._lead_times,
@@ -337,4 +371,30 @@ class MetaNeighbourhood(BasePlugin):
             )(cube)
         else:
             raise ValueError(f"Unknown neighbourhood_output: {self._neighbourhood_output}")
+        if self._degrees_as_complex:
+            # complex_conversion.py:39-69 (complex_to_deg): angle in [0, 360), float32
+            data = result.data
+            angle = np.mod(np.float32(np.angle(np.ma.getdata(data), deg=True)), 360).astype(np.float32)
+            if isinstance(data, np.ma.MaskedArray):
+                angle = np.ma.masked_array(angle, np.ma.getmaskarray(data))
+            result = result.copy(data=angle)
+        if self._halo_radius is not None:
+            result = remove_cube_halo(result, self._halo_radius)
         return result
+
+
+def remove_cube_halo(cube, halo_radius: float):
+    """improver/utilities/pad_spatial.py:222-300: drop `halo_radius` metres of rows / columns from
+    every edge of every 2-D slice and trim the spatial coordinates accordingly."""
+    wx = distance_to_number_of_grid_cells(cube, halo_radius, axis="x")
+    wy = distance_to_number_of_grid_cells(cube, halo_radius, axis="y")
+    ydim = cube.coord_dims(cube.coord(axis="y"))[0]
+    xdim = cube.coord_dims(cube.coord(axis="x"))[0]
+    index = [slice(None)] * len(cube.shape)
+    index[ydim] = slice(wy, -wy if wy else None)
+    index[xdim] = slice(wx, -wx if wx else None)
+    result = cube.copy(data=cube.data[tuple(index)])
+    for axis, w in (("y", wy), ("x", wx)):
+        coord = result.coord(axis=axis)
+        coord.points = coord.points[w:len(coord.points) - w if w else None]
+    return result

@@ -326,3 +326,53 @@ def test_nbhood_land_and_sea_vs_oracle():
         result = nbhood_land_and_sea(cube, mask_cube, neighbourhood_shape=shape, radii=6000)
         exp = orc.land_sea_neighbourhood(data, land, method=shape, cells=cells)
         np.testing.assert_allclose(np.asarray(result.data), exp, atol=1e-5)
+
+
+def test_kat_complex_square():
+    """improver_tests/nbhood/nbhood/test_NeighbourhoodProcessing.py:289-331 (test_complex):
+    complex input is processed component-wise, output complex64."""
+    data = np.ones((5, 5), dtype=complex)
+    data[2, 2] = 0
+    data[1, 3] = 0.5 + 0.5j
+    data[4, 3] = 0.4 + 0.6j
+    expected = np.array([
+        [1.0 + 0.0j, 1.0 + 0.0j, 0.91666667 + 0.083333333j, 0.91666667 + 0.083333333j, 0.875 + 0.125j],
+        [1.0 + 0.0j, 0.88888889 + 0.0j, 0.83333333 + 0.055555556j, 0.83333333 + 0.055555556j, 0.91666667 + 0.083333333j],
+        [1.0 + 0.0j, 0.88888889 + 0.0j, 0.83333333 + 0.055555556j, 0.83333333 + 0.055555556j, 0.91666667 + 0.083333333j],
+        [1.0 + 0.0j, 0.88888889 + 0.0j, 0.82222222 + 0.066666667j, 0.82222222 + 0.066666667j, 0.9 + 0.1j],
+        [1.0 + 0.0j, 1.0 + 0.0j, 0.9 + 0.1j, 0.9 + 0.1j, 0.85 + 0.15j]])
+    plugin = NeighbourhoodProcessing("square", 2500)
+    plugin.nb_size = 3
+    result = plugin._calculate_neighbourhood(data)
+    assert result.dtype == np.complex64
+    np.testing.assert_array_almost_equal(np.ma.getdata(result), expected)
+
+
+def test_meta_neighbourhood_degrees_as_complex_and_halo():
+    """MetaNeighbourhood(degrees_as_complex=True) (nbhood.py:866-889; complex_conversion.py) against
+    the numpy restatement: unit vectors, box mean of the components, angle back in [0, 360); and
+    halo_radius removal (nbhood.py:890-893, pad_spatial.py:222-300)."""
+    from improver_b200.nbhood.nbhood import MetaNeighbourhood
+
+    rng = np.random.default_rng(17)
+    deg = (rng.random((3, 24, 30)) * 360).astype(np.float32)
+    cube = set_up_variable_cube(deg, name="wind_from_direction", units="degrees")
+    result = MetaNeighbourhood("probabilities", 4000, neighbourhood_shape="square", degrees_as_complex=True)(cube)
+    rad = np.deg2rad(deg)
+    z = np.cos(rad) + 1j * np.sin(rad)
+    exp = np.empty(deg.shape, np.float32)
+    for k in range(3):
+        re = np.ma.getdata(orc.neighbourhood(z[k].real.astype(np.float64), None, cells=2, sum_only=True, re_mask=False))
+        im = np.ma.getdata(orc.neighbourhood(z[k].imag.astype(np.float64), None, cells=2, sum_only=True, re_mask=False))
+        exp[k] = np.mod(np.float32(np.angle(re + 1j * im, deg=True)), 360)
+    got = np.ma.getdata(result.data)
+    diff = np.abs(((got - exp) + 180.0) % 360.0 - 180.0)        # angular distance
+    assert float(diff.max()) < 2e-3
+    assert got.dtype == np.float32 and got.min() >= 0.0 and got.max() < 360.0
+
+    prob = set_up_probability_cube(rng.random((2, 24, 30)).astype(np.float32), [1.0, 2.0])
+    full = MetaNeighbourhood("probabilities", 4000)(prob)
+    trimmed = MetaNeighbourhood("probabilities", 4000, halo_radius=6000)(prob)
+    assert trimmed.shape == (2, 18, 24)
+    np.testing.assert_array_equal(np.ma.getdata(trimmed.data), np.ma.getdata(full.data)[:, 3:-3, 3:-3])
+    np.testing.assert_array_equal(trimmed.coord(axis="x").points, full.coord(axis="x").points[3:-3])
