@@ -13,7 +13,9 @@ int env_int(const char* name, int dflt);
 bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid) {
   if (!env_int("NBH_SQ_RS", 1)) return false;
   const int r = d.cells, nb = 2 * r + 1, R = d.n_members;
-  if (R < 2 || (d.flags & NBH_WRAP_X) || d.mask_nd) return false;
+  const bool rows_mode = R == 1;
+  if (rows_mode && !env_int("NBH_SQ_RS_ROWS", 1)) return false;
+  if ((d.flags & NBH_WRAP_X) || d.mask_nd) return false;
   if ((d.nx & 1) || (reinterpret_cast<uintptr_t>(in) & 7) || (d.plane_stride & 1) || (d.member_stride & 3))
     return false;
   const int hl = (r + 1) & ~1;
@@ -24,13 +26,15 @@ bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid) {
   const int n_windows_total = 1 + (d.nx > W0 ? (d.nx - W0 + W - 1) / W : 0);
   const int n_panels = (n_windows_total + kRsMaxWindows - 1) / kRsMaxWindows;
   const int n_windows = (n_windows_total + n_panels - 1) / n_panels;
+  if (rows_mode && n_panels > 1) return false;          // a stage is one contiguous copy of full rows
   int dev = 0, smem_max = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (smem_max <= 0) smem_max = 227 * 1024;
   const int seg_cols = min(d.nx, n_windows * W + hl + r + (W0 - W));    // widest staged segment
-  const int pitch = (seg_cols + 3 + 3) / 4 * 4;        // up to 3 floats of alignment shift
-  const size_t fixed = sq_rs_fixed_smem(nb, n_windows) + 256;
+  const int rps = rows_mode ? max(1, min(kRsBatch, env_int("NBH_SQ_RS_RPS", kRsBatch))) : 0;
+  const int pitch = ((rows_mode ? rps * d.nx : seg_cols) + 3 + 3) / 4 * 4;   // up to 3 floats of alignment shift
+  const size_t fixed = sq_rs_fixed_smem(nb, n_windows, R == 1 ? kRsBatch : 1) + 256;
   if (fixed + 2 * (size_t)pitch * 4 > (size_t)smem_max) return false;
   const size_t avail = (size_t)smem_max - fixed;
   // items per stage: the largest divisor of R whose stage stays below ~1/5 of the ring
@@ -45,7 +49,7 @@ bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid) {
   if (n_stages < 2) return false;
   g->n_windows = n_windows; g->n_panels = n_panels; g->n_windows_total = n_windows_total;
   g->W0 = W0; g->W = W; g->hl = hl;
-  g->ms = ms; g->n_stages = n_stages; g->pitch = pitch;
+  g->ms = ms; g->n_stages = n_stages; g->pitch = pitch; g->rps = rps;
   // fixed-point scale: nb^2 * R * 2^shift < 2^31 (window sums are exact modulo 2^32)
   int shift = 0;
   while (shift < 22 && (double)nb * nb * R * (double)(1u << (shift + 1)) < 2147483648.0) ++shift;
@@ -65,7 +69,7 @@ bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid) {
 template <int TM, bool M2D>
 static int launch_rs_one(const SqParams& p, const SqRsGeom& g, int grid, cudaStream_t st) {
   auto kern = square_rs_kernel<TM, M2D>;
-  const size_t smem = (size_t)g.n_stages * g.ms * g.pitch * 4 + sq_rs_fixed_smem(p.nb, g.n_windows);
+  const size_t smem = (size_t)g.n_stages * g.ms * g.pitch * 4 + sq_rs_fixed_smem(p.nb, g.n_windows, g.rps ? kRsBatch : 1);
   NBH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)grid, (g.n_windows + kRsProducers) * 32, smem, st>>>(p, g);
   NBH_CHECK_CUDA(cudaGetLastError());

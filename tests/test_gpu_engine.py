@@ -338,20 +338,27 @@ def test_row_stream_rows_kernel_matches_oracle(shape, cells, wrap, monkeypatch):
             out, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, sum_only=sum_only, wrap_x=wrap)
             engine.check_status(status)
             monkeypatch.setenv("NBH_SQ_RR", "0")
+            monkeypatch.setenv("NBH_SQ_RS_ROWS", "0")                # the warp kernel
             ref, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, sum_only=sum_only, wrap_x=wrap)
+            engine.check_status(status)
+            monkeypatch.setenv("NBH_SQ_RS_ROWS", "1")                # rows mode of square_rs_kernel (default)
+            rsr, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, sum_only=sum_only, wrap_x=wrap)
             engine.check_status(status)
             scale = max(1.0, float((2 * cells + 1) ** 2)) if sum_only else 1.0
             np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), atol=2e-6 * scale, equal_nan=True)
+            np.testing.assert_allclose(rsr.cpu().numpy(), ref.cpu().numpy(), atol=2e-6 * scale, equal_nan=True)
             exp = _square_oracle_stack(data, m, cells, wrap=wrap, sum_only=sum_only)
             _assert_close(out.cpu().numpy(), exp, atol=ATOL * scale)
+            _assert_close(rsr.cpu().numpy(), exp, atol=ATOL * scale)
     # thresholded single slices (fixed-point sums) against the oracle chain with one member
-    monkeypatch.setenv("NBH_SQ_RR", "1")
     if not wrap:
         gam = rng.gamma(2.0, 1.5, (1,) + flat.shape).astype(np.float32)
-        out, _, status = engine.neighbourhood(_dev(gam[0]), cells, thresholds=[(2.0, 1.4, 2.6, ">")])
-        engine.check_status(status)
         exp = orc.threshold_square_mean(gam, [2.0], [(1.4, 2.6)], ">", cells)
-        _assert_close(out.cpu().numpy()[:, 0], exp[:, 0])
+        for rr in ("1", "0"):
+            monkeypatch.setenv("NBH_SQ_RR", rr)
+            out, _, status = engine.neighbourhood(_dev(gam[0]), cells, thresholds=[(2.0, 1.4, 2.6, ">")])
+            engine.check_status(status)
+            _assert_close(out.cpu().numpy()[:, 0], exp[:, 0])
 
 
 def test_member_padded_device_layout_is_equivalent():
