@@ -16,6 +16,7 @@
 #include "nbh_square_tma.cuh"
 #include "nbh_square_rs.cuh"
 #include "nbh_square_rr.cuh"
+#include "nbh_square_r2.cuh"
 
 namespace nbh {
 
@@ -335,6 +336,7 @@ static bool plan_square_warp(const NbhDesc& d, int vec, SqWarpGeom* g) {
 }
 
 bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid);
+bool plan_square_r2(const NbhDesc& d, const float* in, SqR2Geom* g, int* grid, size_t* smem);
 bool plan_square_rr(const NbhDesc& d, const float* in, int tm, SqRrGeom* g, int* grid, size_t* smem);
 
 bool make_square_tensor_map(const float* in, int ny, int nx, long long n_planes, int n_members,
@@ -502,15 +504,23 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   const bool use_mt = !use_tma && use_warp && pl.vec >= 2 && d->n_members >= 2 && d->n_thresholds >= 2 &&
                       tm >= 1 && !(d->flags & NBH_WRAP_X) && env_int("NBH_SQ_MT", 0) &&   // opt-in: see profiles/r1_multi_threshold.jsonl
                       plan_square_warp(*d, 2, &wgm) && wgm.WS == 64;
+  SqR2Geom r2g;
+  int r2_grid = 0;
+  size_t r2_smem = 0;
+  const bool use_r2 = !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && !use_tma && !use_mt &&
+                      plan_square_r2(*d, in, &r2g, &r2_grid, &r2_smem);
   SqRsGeom rg;
   int rs_grid = 0;
-  const bool use_rs = use_warp && !use_tma && !use_mt && plan_square_rs(*d, in, &rg, &rs_grid);
+  const bool use_rs = !use_r2 && use_warp && !use_tma && !use_mt && plan_square_rs(*d, in, &rg, &rs_grid);
   SqRrGeom rrg;
   int rr_grid = 0;
   size_t rr_smem = 0;
-  const bool use_rr = !use_rs && !use_tma && !use_mt && !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 &&
+  const bool use_rr = !use_r2 && !use_rs && !use_tma && !use_mt && !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 &&
                       plan_square_rr(*d, in, tm_warp, &rrg, &rr_grid, &rr_smem);
-  if (use_rs) {
+  if (use_r2) {
+    ProfileScope prof(st, "nbh::square_r2_kernel (two-phase row-streaming, single-member slices)");
+    rc = launch_square_r2(p, r2g, tm_warp, d->mask2d != nullptr, r2_grid, r2_smem, st);
+  } else if (use_rs) {
     ProfileScope prof(st, "nbh::square_rs_kernel (row-streaming, bulk-copy staged rows)");
     rc = launch_square_rs(p, rg, tm_warp, d->mask2d != nullptr, rs_grid, st);
   } else if (use_rr) {
