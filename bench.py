@@ -75,7 +75,7 @@ class ClockSampler:
                     self.samples.append(parts)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._thr = threading.Thread(target=self._run, daemon=True)
@@ -202,10 +202,10 @@ def run_ours(args):
 
     # ---- device-resident timing (value) -------------------------------------
     # The timed region is a few milliseconds long: nvidia-smi is sampled over a
-    # window that starts ~0.5 s earlier (same kernel, untimed) and spans the region.
+    # window that starts ~0.2 s earlier (same kernel, untimed) and spans the region.
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
-        t_end = time.perf_counter() + 0.5
+        t_end = time.perf_counter() + 0.2
         while time.perf_counter() < t_end:
             for _ in range(20):
                 status = step()
