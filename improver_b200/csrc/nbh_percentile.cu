@@ -68,10 +68,18 @@ __device__ __forceinline__ void select_group(const unsigned (&key)[KPL], const P
                                              long long obase) {
   int kk[U];
   unsigned prefix[U];
+  int lo_cnt[U], hi_cnt[U];          // keys below the bucket / below its upper end: the k-th smallest is in
+                                     // the bucket [prefix, prefix + 2^(bit+1)) while lo_cnt <= k < hi_cnt
 #pragma unroll
-  for (int u = 0; u < U; ++u) { kk[u] = p.k_lo[q0 + u]; prefix[u] = 0; }
+  for (int u = 0; u < U; ++u) { kk[u] = p.k_lo[q0 + u]; prefix[u] = 0; lo_cnt[u] = 0; hi_cnt[u] = p.N; }
 #pragma unroll 1
   for (int bit = 31; bit >= 0; --bit) {
+    // stop as soon as every bucket holds a single key (log2(N) + the shared exponent bits instead
+    // of 32 steps on typical fields; ties keep bisecting to the last bit)
+    bool open_bucket = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) open_bucket = open_bucket || (hi_cnt[u] - lo_cnt[u] > 1);
+    if (!open_bucket) break;
     unsigned cand[U];
     int cnt[U];
 #pragma unroll
@@ -84,8 +92,18 @@ __device__ __forceinline__ void select_group(const unsigned (&key)[KPL], const P
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       cnt[u] = __reduce_add_sync(0xffffffffu, cnt[u]);
-      if (cnt[u] <= kk[u]) prefix[u] = cand[u];
+      if (cnt[u] <= kk[u]) { prefix[u] = cand[u]; lo_cnt[u] = cnt[u]; }
+      else hi_cnt[u] = cnt[u];
     }
+  }
+  // the k-th smallest key is the smallest key not below the prefix (exactly lo_cnt == k keys are
+  // below it once the bucket is down to one key; after 32 steps the prefix is the key itself)
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    unsigned sel = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) if (key[j] >= prefix[u]) sel = min(sel, key[j]);
+    prefix[u] = __reduce_min_sync(0xffffffffu, sel);
   }
 #pragma unroll
   for (int u = 0; u < U; ++u) {
