@@ -504,10 +504,15 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   const bool use_mt = !use_tma && use_warp && pl.vec >= 2 && d->n_members >= 2 && d->n_thresholds >= 2 &&
                       tm >= 1 && !(d->flags & NBH_WRAP_X) && env_int("NBH_SQ_MT", 0) &&   // opt-in: see profiles/r1_multi_threshold.jsonl
                       plan_square_warp(*d, 2, &wgm) && wgm.WS == 64;
+  SqTileGeom tlg;
+  long long tile_blocks = 0;
+  size_t tile_smem = 0;
+  const bool use_tile = !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && !use_tma && !use_mt &&
+                        plan_square_tile(*d, &tlg, &tile_blocks, &tile_smem);
   SqR2Geom r2g;
   int r2_grid = 0;
   size_t r2_smem = 0;
-  const bool use_r2 = !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && !use_tma && !use_mt &&
+  const bool use_r2 = !use_tile && !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && !use_tma && !use_mt &&
                       plan_square_r2(*d, in, &r2g, &r2_grid, &r2_smem);
   SqRsGeom rg;
   int rs_grid = 0;
@@ -517,7 +522,10 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   size_t rr_smem = 0;
   const bool use_rr = !use_r2 && !use_rs && !use_tma && !use_mt && !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 &&
                       plan_square_rr(*d, in, tm_warp, &rrg, &rr_grid, &rr_smem);
-  if (use_r2) {
+  if (use_tile) {
+    ProfileScope prof(st, "nbh::square_tile_kernel (separable running sums in independent tiles)");
+    rc = launch_square_tile(p, tlg, tm_warp, d->mask2d != nullptr, tile_blocks, tile_smem, st);
+  } else if (use_r2) {
     ProfileScope prof(st, "nbh::square_r2_kernel (two-phase row-streaming, single-member slices)");
     rc = launch_square_r2(p, r2g, tm_warp, d->mask2d != nullptr, r2_grid, r2_smem, st);
   } else if (use_rs) {

@@ -334,7 +334,11 @@ def test_row_stream_rows_kernel_matches_oracle(shape, cells, wrap, monkeypatch):
     for m in (None, mask):
         md = _dev(m) if m is not None else None
         for sum_only in (False, True):
-            monkeypatch.setenv("NBH_SQ_R2", "1")                     # two-phase kernel (default)
+            monkeypatch.setenv("NBH_SQ_TILE", "1")                   # tile kernel (default)
+            tl, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, sum_only=sum_only, wrap_x=wrap)
+            engine.check_status(status)
+            monkeypatch.setenv("NBH_SQ_TILE", "0")
+            monkeypatch.setenv("NBH_SQ_R2", "1")                     # two-phase persistent kernel (opt-in)
             r2, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, sum_only=sum_only, wrap_x=wrap)
             engine.check_status(status)
             monkeypatch.setenv("NBH_SQ_R2", "0")
@@ -355,13 +359,15 @@ def test_row_stream_rows_kernel_matches_oracle(shape, cells, wrap, monkeypatch):
             _assert_close(out.cpu().numpy(), exp, atol=ATOL * scale)
             _assert_close(rsr.cpu().numpy(), exp, atol=ATOL * scale)
             _assert_close(r2.cpu().numpy(), exp, atol=ATOL * scale)
+            _assert_close(tl.cpu().numpy(), exp, atol=ATOL * scale)
     # thresholded single slices (fixed-point sums) against the oracle chain with one member
     if not wrap:
         gam = rng.gamma(2.0, 1.5, (1,) + flat.shape).astype(np.float32)
         exp = orc.threshold_square_mean(gam, [2.0], [(1.4, 2.6)], ">", cells)
-        for rr, r2v in (("1", "0"), ("0", "0"), ("0", "1")):
+        for rr, r2v, tlv in (("1", "0", "0"), ("0", "0", "0"), ("0", "1", "0"), ("0", "0", "1")):
             monkeypatch.setenv("NBH_SQ_RR", rr)
             monkeypatch.setenv("NBH_SQ_R2", r2v)
+            monkeypatch.setenv("NBH_SQ_TILE", tlv)
             out, _, status = engine.neighbourhood(_dev(gam[0]), cells, thresholds=[(2.0, 1.4, 2.6, ">")])
             engine.check_status(status)
             _assert_close(out.cpu().numpy()[:, 0], exp[:, 0])
