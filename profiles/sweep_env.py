@@ -15,8 +15,9 @@ cube = torch.empty((R, L, NY, NX), dtype=torch.float32, device=dev)
 for r in range(R):
     u = torch.rand((2, L, NY, NX), generator=g, device=dev).clamp_min_(1e-12)
     cube[r] = -1.5 * (torch.log(u[0]) + torch.log(u[1]))
-out = torch.empty((L, 1, NY, NX), dtype=torch.float32, device=dev)
-thr = [(2.0, 1.4, 2.6, ">")]
+T = int(os.environ.get("SWEEP_T", "1"))
+out = torch.empty((L, T, NY, NX), dtype=torch.float32, device=dev)
+thr = [(v, 0.7 * v, 1.3 * v, ">") for v in (2.0, 1.0, 4.0, 0.5, 6.0, 8.0, 3.0, 5.0)[:T]]
 cells = int(os.environ.get("SWEEP_CELLS", "5"))
 ref = None
 for spec in sys.argv[1:] or [""]:
