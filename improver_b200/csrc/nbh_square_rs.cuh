@@ -4,10 +4,12 @@
 // Why: the warp-autonomous kernel re-reads the x halo of every 64-column strip
 // and the y halo of every y segment (1.23 x 1.17 = 1.44 x the algorithmic bytes
 // at the L1 level for the UK grid, served by L2) and holds its bytes in flight
-// in registers.  Here a block owns FULL rows: a producer lane streams the rows
-// of every member of a contiguous share of the (plane, y) rows into a ring of
-// shared-memory stages with `cp.async.bulk` (UBLKCP) completing on mbarriers,
-// and one consumer warp per 64-column window reads its (overlapping) window of
+// in registers.  Here a block owns FULL rows (or, for rows wider than 20
+// windows, the column segment of one x panel): four producer threads stream the
+// rows of every member of a contiguous share of the (plane, y) rows into a ring
+// of shared-memory stages with `cp.async.bulk` (UBLKCP) completing on mbarriers
+// (one thread issues only one bulk copy per ~400-700 cycles, hence four), and
+// one consumer warp per 64-column window reads its (overlapping) window of
 // every staged row from shared memory.  The x halo therefore costs shared-
 // memory reads only, the y halo is 2r rows per ~236-row share (1.05 x), the
 // bytes in flight are bounded by the ~150 KB stage ring instead of registers,
@@ -20,14 +22,21 @@
 // reading the stage.  The widened copy never leaves the 16-byte blocks that
 // hold the row, so it cannot touch an unmapped page.
 //
-// Work split: the n_units * ny output rows (unit = plane x threshold) are cut
-// into gridDim.x equal contiguous shares; a share may straddle units and is
-// processed piece by piece.  Odd blocks march upwards so the 2r halo rows two
-// neighbouring shares have in common are read at about the same time (L2 hit).
+// Work split: the n_units * ny output rows (unit = plane x threshold x panel)
+// are cut into gridDim.x equal contiguous shares; a share may straddle units
+// and is processed piece by piece.  Odd blocks march upwards so the 2r halo
+// rows two neighbouring shares have in common are read at about the same time
+// (L2 hit).
 //
-// Arithmetic is that of square_warp_kernel: float32 member
-// sum, float64 vertical running sums over a warp-private shared-memory ring,
-// float64 warp-shuffle scan + prefix difference, reciprocal-table normalise.
+// Two modes.  Members mode (n_members >= 2, the fused threshold -> box sum ->
+// realization mean): a stage holds `ms` member rows of one grid row.  Rows mode
+// (n_members == 1): consecutive rows of a slice are contiguous, a stage is ONE
+// copy of up to four rows, and the rows of a stage are processed as a batch so
+// that their scans interleave.
+//
+// Arithmetic: float32 member sum; thresholded launches then use exact unsigned
+// fixed-point vertical / horizontal window sums (see the consumer section),
+// raw-data launches the float64 sums of square_warp_kernel.
 #pragma once
 #include "nbh_square_tma.cuh"
 
