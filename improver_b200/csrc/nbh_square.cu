@@ -15,8 +15,6 @@
 #include "nbh_square_mt.cuh"
 #include "nbh_square_tma.cuh"
 #include "nbh_square_rs.cuh"
-#include "nbh_square_rr.cuh"
-#include "nbh_square_r2.cuh"
 
 namespace nbh {
 
@@ -336,8 +334,6 @@ static bool plan_square_warp(const NbhDesc& d, int vec, SqWarpGeom* g) {
 }
 
 bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid);
-bool plan_square_r2(const NbhDesc& d, const float* in, SqR2Geom* g, int* grid, size_t* smem);
-bool plan_square_rr(const NbhDesc& d, const float* in, int tm, SqRrGeom* g, int* grid, size_t* smem);
 
 bool make_square_tensor_map(const float* in, int ny, int nx, long long n_planes, int n_members,
                             long long plane_stride, long long member_stride, int box_cols, CUtensorMap* map,
@@ -509,31 +505,15 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   size_t tile_smem = 0;
   const bool use_tile = !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && !use_tma && !use_mt &&
                         plan_square_tile(*d, &tlg, &tile_blocks, &tile_smem);
-  SqR2Geom r2g;
-  int r2_grid = 0;
-  size_t r2_smem = 0;
-  const bool use_r2 = !use_tile && !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && !use_tma && !use_mt &&
-                      plan_square_r2(*d, in, &r2g, &r2_grid, &r2_smem);
   SqRsGeom rg;
   int rs_grid = 0;
-  const bool use_rs = !use_r2 && use_warp && !use_tma && !use_mt && plan_square_rs(*d, in, &rg, &rs_grid);
-  SqRrGeom rrg;
-  int rr_grid = 0;
-  size_t rr_smem = 0;
-  const bool use_rr = !use_r2 && !use_rs && !use_tma && !use_mt && !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 &&
-                      plan_square_rr(*d, in, tm_warp, &rrg, &rr_grid, &rr_smem);
+  const bool use_rs = !use_tile && use_warp && !use_tma && !use_mt && plan_square_rs(*d, in, &rg, &rs_grid);
   if (use_tile) {
     ProfileScope prof(st, "nbh::square_tile_kernel (separable running sums in independent tiles)");
     rc = launch_square_tile(p, tlg, tm_warp, d->mask2d != nullptr, tile_blocks, tile_smem, st);
-  } else if (use_r2) {
-    ProfileScope prof(st, "nbh::square_r2_kernel (two-phase row-streaming, single-member slices)");
-    rc = launch_square_r2(p, r2g, tm_warp, d->mask2d != nullptr, r2_grid, r2_smem, st);
   } else if (use_rs) {
     ProfileScope prof(st, "nbh::square_rs_kernel (row-streaming, bulk-copy staged rows)");
     rc = launch_square_rs(p, rg, tm_warp, d->mask2d != nullptr, rs_grid, st);
-  } else if (use_rr) {
-    ProfileScope prof(st, "nbh::square_rr_kernel (row-streaming, single-member slices)");
-    rc = launch_square_rr(p, rrg, tm_warp, d->mask2d != nullptr, rr_grid, rr_smem, st);
   } else if (use_mt) {
     // tasks do not include the threshold index: re-plan the y segmentation for 12 warps / SM
     const long long units = d->n_planes * (long long)wgm.n_strips;

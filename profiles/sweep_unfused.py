@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Time the un-fused square neighbourhood (single-member slices) under env settings.
-usage: SWEEP_SHAPE=240,970,1042 python profiles/sweep_unfused.py "NBH_SQ_RR=1" "NBH_SQ_RR=0" ..."""
+usage: SWEEP_SHAPE=240,970,1042 python profiles/sweep_unfused.py "NBH_SQ_TILE=1" "NBH_SQ_RS_ROWS=0" ..."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -316,10 +316,10 @@ def _square_oracle_stack(data, mask, cells, wrap=False, sum_only=False):
                                               ((2, 3, 33, 58), 2, False), ((7, 64, 64), 1, False),
                                               ((2, 30, 1400), 3, False), ((3, 50, 256), 5, True),
                                               ((2, 24, 1480), 4, True), ((4, 51, 700), 9, False)])
-def test_row_stream_rows_kernel_matches_oracle(shape, cells, wrap, monkeypatch):
-    """Row-streaming kernel for single-member slices (default un-fused square path):
-    oracle parity with / without an external mask, sum_only, periodic x, x panels
-    (nx > 12 windows), ones-trimming slices, and equality with the warp kernel."""
+def test_single_member_kernels_match_oracle(shape, cells, wrap, monkeypatch):
+    """Single-member slices (the un-fused square path): rows mode of the row-streaming kernel
+    (default where eligible), the tile kernel (opt-in) and the warp kernel against the oracle with
+    / without an external mask, sum_only, periodic x, wide rows and ones-trimming slices."""
     from improver_b200 import engine
 
     rng = np.random.default_rng(43)
@@ -331,43 +331,27 @@ def test_row_stream_rows_kernel_matches_oracle(shape, cells, wrap, monkeypatch):
         flat[-1] = 1.0
         flat[-1, 10:12, -3:] = 0.0
     mask = (rng.random(shape[-2:]) < 0.8).astype(np.uint8)
+    variants = {"rows": {"NBH_SQ_TILE": "0", "NBH_SQ_RS_ROWS": "1"},
+                "tile": {"NBH_SQ_TILE": "1", "NBH_SQ_RS_ROWS": "1"},
+                "warp": {"NBH_SQ_TILE": "0", "NBH_SQ_RS_ROWS": "0"}}
     for m in (None, mask):
         md = _dev(m) if m is not None else None
         for sum_only in (False, True):
-            monkeypatch.setenv("NBH_SQ_TILE", "1")                   # tile kernel (default)
-            tl, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, sum_only=sum_only, wrap_x=wrap)
-            engine.check_status(status)
-            monkeypatch.setenv("NBH_SQ_TILE", "0")
-            monkeypatch.setenv("NBH_SQ_R2", "1")                     # two-phase persistent kernel (opt-in)
-            r2, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, sum_only=sum_only, wrap_x=wrap)
-            engine.check_status(status)
-            monkeypatch.setenv("NBH_SQ_R2", "0")
-            monkeypatch.setenv("NBH_SQ_RR", "1")
-            out, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, sum_only=sum_only, wrap_x=wrap)
-            engine.check_status(status)
-            monkeypatch.setenv("NBH_SQ_RR", "0")
-            monkeypatch.setenv("NBH_SQ_RS_ROWS", "0")                # the warp kernel
-            ref, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, sum_only=sum_only, wrap_x=wrap)
-            engine.check_status(status)
-            monkeypatch.setenv("NBH_SQ_RS_ROWS", "1")                # rows mode of square_rs_kernel (default)
-            rsr, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, sum_only=sum_only, wrap_x=wrap)
-            engine.check_status(status)
             scale = max(1.0, float((2 * cells + 1) ** 2)) if sum_only else 1.0
-            np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), atol=2e-6 * scale, equal_nan=True)
-            np.testing.assert_allclose(rsr.cpu().numpy(), ref.cpu().numpy(), atol=2e-6 * scale, equal_nan=True)
             exp = _square_oracle_stack(data, m, cells, wrap=wrap, sum_only=sum_only)
-            _assert_close(out.cpu().numpy(), exp, atol=ATOL * scale)
-            _assert_close(rsr.cpu().numpy(), exp, atol=ATOL * scale)
-            _assert_close(r2.cpu().numpy(), exp, atol=ATOL * scale)
-            _assert_close(tl.cpu().numpy(), exp, atol=ATOL * scale)
-    # thresholded single slices (fixed-point sums) against the oracle chain with one member
+            for name, env in variants.items():
+                for k, v in env.items():
+                    monkeypatch.setenv(k, v)
+                out, _, status = engine.neighbourhood(_dev(data), cells, mask2d=md, sum_only=sum_only, wrap_x=wrap)
+                engine.check_status(status)
+                _assert_close(out.cpu().numpy(), exp, atol=ATOL * scale)
+    # thresholded single slices against the oracle chain with one member
     if not wrap:
         gam = rng.gamma(2.0, 1.5, (1,) + flat.shape).astype(np.float32)
         exp = orc.threshold_square_mean(gam, [2.0], [(1.4, 2.6)], ">", cells)
-        for rr, r2v, tlv in (("1", "0", "0"), ("0", "0", "0"), ("0", "1", "0"), ("0", "0", "1")):
-            monkeypatch.setenv("NBH_SQ_RR", rr)
-            monkeypatch.setenv("NBH_SQ_R2", r2v)
-            monkeypatch.setenv("NBH_SQ_TILE", tlv)
+        for name, env in variants.items():
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
             out, _, status = engine.neighbourhood(_dev(gam[0]), cells, thresholds=[(2.0, 1.4, 2.6, ">")])
             engine.check_status(status)
             _assert_close(out.cpu().numpy()[:, 0], exp[:, 0])
