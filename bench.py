@@ -134,6 +134,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    cores = max(1, min(cores, int(os.environ.get("NBH_BENCH_REF_PROCS", cores))))   # tests shrink the sample
     vals = []
     sample = ""
     for _ in range(args.warmup):
