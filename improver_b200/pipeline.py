@@ -121,6 +121,27 @@ def threshold_neighbourhood_mean_host(host_in, thresholds: Sequence[float], boun
     return out_host
 
 
+class GraphedCall:
+    """A native call sequence captured once into a CUDA graph and replayed.
+
+    The fused call is one memset and five kernels, four of them tiny (trimming fix-up
+    bookkeeping): replayed from a graph they run back to back without per-launch gaps
+    (~0.03 ms of a 0.5 ms step).  `fn` must only use tensors that stay alive and must not
+    synchronise; its return value (e.g. the status tensor) is kept as `result`."""
+
+    def __init__(self, fn, warmup: int = 2):
+        for _ in range(warmup):                # allocate workspaces / module state outside the capture
+            fn()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = fn()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.result
+
+
 def time_main_kernel(fn, reps: int = 5) -> float:
     """Average duration (ms) of the dominant kernel of `fn()`'s native call,
     measured with CUDA events recorded inside the library on the launching

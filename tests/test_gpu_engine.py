@@ -374,3 +374,26 @@ def test_member_padded_device_layout_is_equivalent():
     engine.check_status(st)
     np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
     _assert_close(a.cpu().numpy(), orc.threshold_square_mean(data, [2.0], [(1.4, 2.6)], ">", 4))
+
+
+def test_graphed_call_replays_the_fused_chain():
+    """pipeline.GraphedCall (what bench.py times): the fused call captured in a CUDA graph gives
+    the same result as the eager call, also after the input buffer is refilled."""
+    from improver_b200 import engine, pipeline
+
+    rng = np.random.default_rng(71)
+    data = rng.gamma(2.0, 1.5, (6, 2, 80, 130)).astype(np.float32)
+    cube = _dev(data)
+    out = torch.empty((2, 1, 80, 130), dtype=torch.float32, device="cuda")
+    thr = [(2.0, 1.4, 2.6, ">")]
+
+    def step():
+        return engine.neighbourhood(cube, 4, thresholds=thr, collapse_members=True, out=out)[2]
+
+    graphed = pipeline.GraphedCall(step)
+    engine.check_status(graphed())
+    _assert_close(out.cpu().numpy(), orc.threshold_square_mean(data, [2.0], [(1.4, 2.6)], ">", 4))
+    data2 = rng.gamma(2.0, 1.5, data.shape).astype(np.float32)
+    cube.copy_(torch.from_numpy(data2))
+    engine.check_status(graphed())
+    _assert_close(out.cpu().numpy(), orc.threshold_square_mean(data2, [2.0], [(1.4, 2.6)], ">", 4))
