@@ -313,6 +313,14 @@ __global__ void __launch_bounds__(256) circ_gather_kernel(const CircGlobalParams
   const double* pre = p.prefix + (long long)b * per_plane;
   const double* cpre = p.cprefix ? p.cprefix + (long long)b * per_plane : nullptr;
   double S = 0.0, A = 0.0;
+  if (!(p.flags & NBH_WRAP_X) && !cpre && x - p.r - 1 >= 0 && x + p.r <= p.nx - 1) {
+    // every span lies inside the row: two loads and two adds per kernel row
+    for (int dy = -p.r; dy <= p.r; ++dy) {
+      const int w = wtab_s[dy < 0 ? -dy : dy];
+      const double* row = pre + (long long)min(max(y + dy, 0), p.ny - 1) * p.nx + x;
+      S += row[w] - row[-w - 1];
+    }
+  } else
   for (int dy = -p.r; dy <= p.r; ++dy) {
     const int w = wtab_s[dy < 0 ? -dy : dy];
     const int ys = min(max(y + dy, 0), p.ny - 1);
@@ -382,16 +390,25 @@ __global__ void __launch_bounds__(256) circ_gather_tiled_kernel(const CircGlobal
     const int y = y0 + ly;
     if (y >= p.ny) break;
     double S = 0.0;
-    for (int dy = -r; dy <= r; ++dy) {
-      const int w = wtab_s[dy < 0 ? -dy : dy];
-      const double* row = tile + (size_t)(ly + r + dy) * TC + cshift;   // indexable by global column >= -1
-      if (p.flags & NBH_WRAP_X) { S += row[x + w] - row[x - w - 1]; continue; }
-      const int lo = max(x - w, 0), hi = min(x + w, p.nx - 1);
-      double s = row[hi] - row[lo - 1];
-      const int nl = lo - (x - w), nr = (x + w) - hi;             // replicated edge cells (mode="nearest")
-      if (nl > 0) s += (double)nl * (row[0] - row[-1]);
-      if (nr > 0) s += (double)nr * (row[p.nx - 1] - row[p.nx - 2]);
-      S += s;
+    if ((p.flags & NBH_WRAP_X) || (x - r - 1 >= -1 && x + r <= p.nx - 1)) {
+      // every span lies inside the row (or the axis is periodic): two loads and two adds per kernel row
+      const double* row = tile + (size_t)ly * TC + cshift + x;
+      for (int dy = -r; dy <= r; ++dy) {
+        const int w = wtab_s[dy < 0 ? -dy : dy];
+        S += row[w] - row[-w - 1];
+        row += TC;
+      }
+    } else {
+      for (int dy = -r; dy <= r; ++dy) {
+        const int w = wtab_s[dy < 0 ? -dy : dy];
+        const double* row = tile + (size_t)(ly + r + dy) * TC + cshift;   // indexable by global column >= -1
+        const int lo = max(x - w, 0), hi = min(x + w, p.nx - 1);
+        double s = row[hi] - row[lo - 1];
+        const int nl = lo - (x - w), nr = (x + w) - hi;             // replicated edge cells (mode="nearest")
+        if (nl > 0) s += (double)nl * (row[0] - row[-1]);
+        if (nr > 0) s += (double)nr * (row[p.nx - 1] - row[p.nx - 2]);
+        S += s;
+      }
     }
     const long long pt = (long long)y * p.nx + x;
     const long long o = (plane * p.n_thr + p.t) * per_plane + pt;
