@@ -504,7 +504,7 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   long long tile_blocks = 0;
   size_t tile_smem = 0;
   const bool use_tile = !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && !use_tma && !use_mt &&
-                        plan_square_tile(*d, &tlg, &tile_blocks, &tile_smem);
+                        plan_square_tile(*d, in, &tlg, &tile_blocks, &tile_smem);
   SqRsGeom rg;
   int rs_grid = 0;
   const bool use_rs = !use_tile && use_warp && !use_tma && !use_mt && plan_square_rs(*d, in, &rg, &rs_grid);

@@ -42,8 +42,9 @@ struct SqTileGeom {
   int tiles_x, tiles_y;
   int sw;                // staged row pitch (floats)
   int n_cnt;             // entries of the reciprocal table: (2r+1)^2
+  int vec2;              // rows are 8-byte aligned: interior tiles load and stage float2
 };
-bool plan_square_tile(const NbhDesc& d, SqTileGeom* g, long long* blocks, size_t* smem);
+bool plan_square_tile(const NbhDesc& d, const float* in, SqTileGeom* g, long long* blocks, size_t* smem);
 int launch_square_tile(const SqParams& p, const SqTileGeom& g, int tm, bool m2d, long long blocks, size_t smem,
                        cudaStream_t st);
 

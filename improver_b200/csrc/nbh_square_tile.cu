@@ -37,6 +37,7 @@ square_tile_kernel(const __grid_constant__ SqParams p, const SqTileGeom g) {
   extern __shared__ __align__(16) float tsm[];
   const int r = p.r, nb = p.nb, nx = p.nx, ny = p.ny;
   const int SW = g.sw, SH = kTileTY + 2 * r;
+  const int ro = r + (r & 1);                           // staged column of output column 0 (window starts on an even column)
   float* stage = tsm;                                   // [SH][SW]: P = valid ? truth_value(d) : 0
   float* hbuf = stage + (size_t)SH * SW;                // [SH][kTileTX]
   float* rcp = hbuf + (size_t)SH * kTileTX;             // [n_cnt + 1]: RN(1 / n)
@@ -58,14 +59,28 @@ square_tile_kernel(const __grid_constant__ SqParams p, const SqTileGeom g) {
   // ---- load: window rows y0 - r .. y0 + TY - 1 + r, columns x0 - r .. x0 + TX - 1 + r ----
   float nanacc = 0.f;
   unsigned bits = 0;
-  const int WC = kTileTX + 2 * r;
+  const int WC = kTileTX + r + ro + (r & 1);            // staged columns (even: float2 granularity)
+  const int xs0 = x0 - ro;                              // first staged column
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // tiles whose whole window lies inside the domain and outside the four edge bands (most of
   // them) take a path without bounds tests, wrap arithmetic or flag bookkeeping
   const bool fast = !M2D && (y0 - r > r) && (y0 + kTileTY - 1 + r < ny - 1 - r) &&
-                    (x0 - r > r) && (x0 + kTileTX - 1 + r < nx - 1 - r);
-  if (fast) {
-    const float* wsrc = src + (long long)(y0 - r) * nx + (x0 - r);
+                    (xs0 > r) && (xs0 + WC - 1 < nx - 1 - r);
+  if (fast && g.vec2) {
+    // 8-byte loads and stores: the window starts on an even column of 8-byte aligned rows
+    const float* wsrc = src + (long long)(y0 - r) * nx + xs0;
+    for (int sy = warp; sy < SH; sy += kTileThreads / 32) {
+      const float2* grow = reinterpret_cast<const float2*>(wsrc + (long long)sy * nx);
+      float2* srow = reinterpret_cast<float2*>(stage + sy * SW);
+      for (int sx = lane; sx < WC / 2; sx += 32) {
+        const float2 d = __ldg(grow + sx);
+        nanacc = max_nan(nanacc, fabsf(d.x));
+        nanacc = max_nan(nanacc, fabsf(d.y));
+        srow[sx] = make_float2(truth_value_sum<TM>(d.x, thr), truth_value_sum<TM>(d.y, thr));
+      }
+    }
+  } else if (fast) {
+    const float* wsrc = src + (long long)(y0 - r) * nx + xs0;
     for (int sy = warp; sy < SH; sy += kTileThreads / 32) {
       const float* grow = wsrc + (long long)sy * nx;
       float* srow = stage + sy * SW;
@@ -79,7 +94,7 @@ square_tile_kernel(const __grid_constant__ SqParams p, const SqTileGeom g) {
     // general path: rows / columns outside the domain are zeros (or the periodic continuation);
     // the flag bookkeeping only runs for rows in the top / bottom band and, in tiles that reach
     // the left / right band, for their band columns
-    const bool lr_tile = !sum_only && !wrap && ((x0 - r <= r) || (x0 + kTileTX - 1 + r >= nx - 1 - r));
+    const bool lr_tile = !sum_only && !wrap && ((xs0 <= r) || (xs0 + WC - 1 >= nx - 1 - r));
     for (int sy = warp; sy < SH; sy += kTileThreads / 32) {          // a warp per staged row
       const int y = y0 - r + sy;
       float* srow = stage + sy * SW;
@@ -91,7 +106,7 @@ square_tile_kernel(const __grid_constant__ SqParams p, const SqTileGeom g) {
       const unsigned row_bits = sum_only ? 0u : ((y <= r ? 1u : 0u) | (y >= ny - 1 - r ? 2u : 0u));
       const bool flag_row = row_bits != 0u || lr_tile;
       for (int sx = lane; sx < WC; sx += 32) {
-        int x = x0 - r + sx;
+        int x = xs0 + sx;
         if (wrap) { if (x < 0) x += nx; else if (x >= nx) x -= nx; }
         float v = 0.f;
         if (x >= 0 && x < nx) {
@@ -120,7 +135,7 @@ square_tile_kernel(const __grid_constant__ SqParams p, const SqTileGeom g) {
   constexpr int RUNS = kTileTX / kTileRun;
   for (int task = threadIdx.x; task < SH * RUNS; task += kTileThreads) {
     const int sy = task / RUNS, run = task - sy * RUNS;
-    const float* row = stage + sy * SW + run * kTileRun + r;      // row[c] = staged column of output column c
+    const float* row = stage + sy * SW + run * kTileRun + ro;     // row[c] = staged column of output column c
     float* hrow = hbuf + sy * kTileTX + run * kTileRun;
     float S = 0.f;
     for (int dx = -r; dx <= r; ++dx) S += row[dx];
@@ -188,22 +203,23 @@ square_tile_kernel(const __grid_constant__ SqParams p, const SqTileGeom g) {
 
 // Eligibility: single-member launches without a masked-array input and a radius whose window
 // (two buffers of (TY + 2r) rows) fits comfortably in shared memory.
-bool plan_square_tile(const NbhDesc& d, SqTileGeom* g, long long* blocks, size_t* smem) {
-  // opt-in: on par with the rows mode of square_rs_kernel for raw slices (1.04 vs 1.08 ms on 240 UK
-  // slices) and slower with an external mask (1.77 vs 1.49 ms); issue-bound at ~100 instructions per
-  // point once the address arithmetic of the tile loads and the edge tiles are counted
-  if (!env_int("NBH_SQ_TILE", 0)) return false;
+bool plan_square_tile(const NbhDesc& d, const float* in, SqTileGeom* g, long long* blocks, size_t* smem) {
+  // default for single-member launches without an external mask (0.92 vs 1.08 ms for the rows mode
+  // of square_rs_kernel on 240 UK slices, 0.76 vs 1.20 ms on 48 periodic 1920 x 2560 slices); with a
+  // mask the float64 count plane makes it slower than the rows mode (1.77 vs 1.49 ms), so masked
+  // launches only come here when forced (NBH_SQ_TILE=2)
+  const int mode = env_int("NBH_SQ_TILE", 1);
+  if (mode == 0 || (d.mask2d && mode != 2)) return false;
   const int r = d.cells, nb = 2 * r + 1;
   if (d.n_members != 1 || d.mask_nd || r > 16 || d.nx < 2 * r + 2) return false;
   g->tiles_x = (d.nx + kTileTX - 1) / kTileTX;
   g->tiles_y = (d.ny + kTileTY - 1) / kTileTY;
-  int sw = kTileTX + 2 * r;
-  if ((sw & 1) == 0) ++sw;                               // odd pitch: rows start on different banks
-  g->sw = sw;
+  g->sw = kTileTX + 2 * r + 2 * (r & 1) + 2;             // even pitch (8-byte stores), >= staged columns
+  g->vec2 = ((d.nx & 1) == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0 && (d.plane_stride & 1) == 0) ? 1 : 0;
   g->n_cnt = nb * nb;
   *blocks = d.n_planes * (long long)max(d.n_thresholds, 1) * g->tiles_x * g->tiles_y;
   if (*blocks >= (1LL << 31)) return false;
-  *smem = ((size_t)(kTileTY + 2 * r) * (sw + kTileTX) + g->n_cnt + 1) * 4 + 16;
+  *smem = ((size_t)(kTileTY + 2 * r) * (g->sw + kTileTX) + g->n_cnt + 1) * 4 + 16;
   return true;
 }
 
