@@ -79,6 +79,27 @@ square_tile_kernel(const __grid_constant__ SqParams p, const SqTileGeom g) {
         srow[sx] = make_float2(truth_value_sum<TM>(d.x, thr), truth_value_sum<TM>(d.y, thr));
       }
     }
+  } else if (!M2D && g.vec2 && (xs0 > r) && (xs0 + WC - 1 < nx - 1 - r)) {
+    // tiles at the top / bottom of the domain only: all columns are valid and outside the left /
+    // right bands, so rows are either zeros (outside the domain) or plain 8-byte loads; rows in
+    // the top / bottom band also feed the trimming flags
+    for (int sy = warp; sy < SH; sy += kTileThreads / 32) {
+      const int y = y0 - r + sy;
+      float2* srow = reinterpret_cast<float2*>(stage + sy * SW);
+      if (y < 0 || y >= ny) {
+        for (int sx = lane; sx < WC / 2; sx += 32) srow[sx] = make_float2(0.f, 0.f);
+        continue;
+      }
+      const float2* grow = reinterpret_cast<const float2*>(src + (long long)y * nx + xs0);
+      const unsigned row_bits = sum_only ? 0u : ((y <= r ? 1u : 0u) | (y >= ny - 1 - r ? 2u : 0u));
+      for (int sx = lane; sx < WC / 2; sx += 32) {
+        const float2 d = __ldg(grow + sx);
+        nanacc = max_nan(nanacc, fabsf(d.x));
+        nanacc = max_nan(nanacc, fabsf(d.y));
+        srow[sx] = make_float2(truth_value_sum<TM>(d.x, thr), truth_value_sum<TM>(d.y, thr));
+        if (row_bits && (truth_not_one(d.x, thr) || truth_not_one(d.y, thr))) bits |= row_bits;
+      }
+    }
   } else if (fast) {
     const float* wsrc = src + (long long)(y0 - r) * nx + xs0;
     for (int sy = warp; sy < SH; sy += kTileThreads / 32) {
