@@ -195,13 +195,14 @@ __global__ void count_rows_kernel(const uint8_t* mask, uint16_t* tmp, int ny, in
   }
   tmp[i] = (uint16_t)c;
 }
-__global__ void count_cols_kernel(const uint16_t* tmp, double* rcp, int ny, int nx, int r) {
+__global__ void count_cols_kernel(const uint16_t* tmp, double* rcp, float* cnt_f, int ny, int nx, int r) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)ny * nx) return;
   const int y = (int)(i / nx), x = (int)(i % nx);
   int c = 0;
   for (int yy = max(0, y - r); yy <= min(ny - 1, y + r); ++yy) c += tmp[(long long)yy * nx + x];
   rcp[i] = 1.0 / (double)c;       // +inf where no valid cell: 0 * inf = NaN (nbhood.py:309-311)
+  cnt_f[i] = (float)c;            // the count itself, for the float32 quotient of the tile kernel
 }
 
 // ---------------------------------------------------------------------------
@@ -346,6 +347,7 @@ struct SqWorkspace {
   int* n_suspects;
   CUtensorMap* tmap;
   double* rcp_count;
+  float* cnt_plane;
   uint16_t* tmp;
   size_t total;
 };
@@ -361,6 +363,7 @@ static void carve_workspace(const NbhDesc& d, void* ws, SqWorkspace* w) {
   w->tmap = reinterpret_cast<CUtensorMap*>(base + off); off = align_up(off + sizeof(CUtensorMap), 256);
   w->rcp_count = reinterpret_cast<double*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 8, 256);
   w->tmp = reinterpret_cast<uint16_t*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 2, 256);
+  w->cnt_plane = reinterpret_cast<float*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 4, 256);
   w->total = off;
 }
 
@@ -413,7 +416,7 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   int tm = 0;
   if (fill_thresholds(*d, &p.thr, &tm)) return 1;
   p.in = in; p.out = out; p.out_mask = out_mask;
-  p.mask2d = d->mask2d; p.mask_nd = d->mask_nd; p.rcp_count = w.rcp_count;
+  p.mask2d = d->mask2d; p.mask_nd = d->mask_nd; p.rcp_count = w.rcp_count; p.cnt_plane = w.cnt_plane;
   p.status = status; p.edge_flags = w.edge_flags; p.stats = w.stats;
   p.plane_stride = d->plane_stride; p.member_stride = d->member_stride;
   p.n_planes = d->n_planes; p.n_members = d->n_members;
@@ -438,7 +441,7 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
     const long long n = (long long)d->ny * d->nx;
     count_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d->mask2d, w.tmp, d->ny, d->nx,
                                                                  d->cells, (d->flags & NBH_WRAP_X) ? 1 : 0);
-    count_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.tmp, w.rcp_count, d->ny, d->nx,
+    count_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.tmp, w.rcp_count, w.cnt_plane, d->ny, d->nx,
                                                                  d->cells);
   }
   const long long blocks = (long long)pl.n_strips * pl.n_ysegs * p.n_thr * d->n_planes;

@@ -18,6 +18,7 @@ struct SqParams {
   const uint8_t* mask2d;
   const uint8_t* mask_nd;
   const double* rcp_count;   // (ny,nx) 1/count for mask2d launches
+  const float* cnt_plane;    // (ny,nx) the count itself (float32), same launches
   int32_t* status;
   unsigned* edge_flags;      // [(plane*R + m) * T + t]
   SliceStats* stats;

@@ -64,19 +64,26 @@ square_tile_kernel(const __grid_constant__ SqParams p, const SqTileGeom g) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // tiles whose whole window lies inside the domain and outside the four edge bands (most of
   // them) take a path without bounds tests, wrap arithmetic or flag bookkeeping
-  const bool fast = !M2D && (y0 - r > r) && (y0 + kTileTY - 1 + r < ny - 1 - r) &&
+  const bool fast = (y0 - r > r) && (y0 + kTileTY - 1 + r < ny - 1 - r) &&
                     (xs0 > r) && (xs0 + WC - 1 < nx - 1 - r);
   if (fast && g.vec2) {
     // 8-byte loads and stores: the window starts on an even column of 8-byte aligned rows
     const float* wsrc = src + (long long)(y0 - r) * nx + xs0;
     for (int sy = warp; sy < SH; sy += kTileThreads / 32) {
       const float2* grow = reinterpret_cast<const float2*>(wsrc + (long long)sy * nx);
+      const uchar2* mrow = M2D ? reinterpret_cast<const uchar2*>(p.mask2d + (long long)(y0 - r + sy) * nx + xs0) : nullptr;
       float2* srow = reinterpret_cast<float2*>(stage + sy * SW);
       for (int sx = lane; sx < WC / 2; sx += 32) {
         const float2 d = __ldg(grow + sx);
         nanacc = max_nan(nanacc, fabsf(d.x));
         nanacc = max_nan(nanacc, fabsf(d.y));
-        srow[sx] = make_float2(truth_value_sum<TM>(d.x, thr), truth_value_sum<TM>(d.y, thr));
+        float2 v = make_float2(truth_value_sum<TM>(d.x, thr), truth_value_sum<TM>(d.y, thr));
+        if (M2D) {
+          const uchar2 m = __ldg(mrow + sx);
+          v.x = m.x ? v.x : 0.f;
+          v.y = m.y ? v.y : 0.f;
+        }
+        srow[sx] = v;
       }
     }
   } else if (!M2D && g.vec2 && (xs0 > r) && (xs0 + WC - 1 < nx - 1 - r)) {
@@ -104,11 +111,13 @@ square_tile_kernel(const __grid_constant__ SqParams p, const SqTileGeom g) {
     const float* wsrc = src + (long long)(y0 - r) * nx + xs0;
     for (int sy = warp; sy < SH; sy += kTileThreads / 32) {
       const float* grow = wsrc + (long long)sy * nx;
+      const uint8_t* mrow = M2D ? p.mask2d + (long long)(y0 - r + sy) * nx + xs0 : nullptr;
       float* srow = stage + sy * SW;
       for (int sx = lane; sx < WC; sx += 32) {
         const float d = __ldg(grow + sx);
         nanacc = max_nan(nanacc, fabsf(d));
-        srow[sx] = truth_value_sum<TM>(d, thr);
+        const float v = truth_value_sum<TM>(d, thr);
+        srow[sx] = (!M2D || mrow[sx]) ? v : 0.f;
       }
     }
   } else {
@@ -183,7 +192,7 @@ square_tile_kernel(const __grid_constant__ SqParams p, const SqTileGeom g) {
   float V = 0.f;
   for (int k = 0; k < nb; ++k) V += hcol[k * kTileTX];
   float* optr = p.out + obase + (long long)ya * nx + x;
-  if (fast && !sum_only && !p.out_mask) {
+  if (fast && !sum_only && !p.out_mask && !M2D) {
     // every window is complete: one count, one reciprocal
     const float cnt = (float)(nb * nb), rc = rcp[nb * nb];
     for (int y = ya; y < yb; ++y) {
@@ -208,7 +217,10 @@ square_tile_kernel(const __grid_constant__ SqParams p, const SqTileGeom g) {
     if (sum_only) {
       o = V;
     } else if (M2D) {
-      o = (float)((double)V * p.rcp_count[pt]);
+      // count of valid cells from the count plane; no valid cell -> NaN (nbhood.py:309-311)
+      const float cnt = p.cnt_plane[pt], rc = rcp[(int)cnt];
+      const float q = V * rc;
+      o = cnt > 0.f ? fmaf(fmaf(-q, cnt, V), rc, q) : __int_as_float(0x7fc00000);
     } else {
       const int rows_in = min(y + r, ny - 1) - max(y - r, 0) + 1;
       const float cnt = (float)(rows_in * cols_in), rc = rcp[rows_in * cols_in];
@@ -225,12 +237,9 @@ square_tile_kernel(const __grid_constant__ SqParams p, const SqTileGeom g) {
 // Eligibility: single-member launches without a masked-array input and a radius whose window
 // (two buffers of (TY + 2r) rows) fits comfortably in shared memory.
 bool plan_square_tile(const NbhDesc& d, const float* in, SqTileGeom* g, long long* blocks, size_t* smem) {
-  // default for single-member launches without an external mask (0.92 vs 1.08 ms for the rows mode
-  // of square_rs_kernel on 240 UK slices, 0.76 vs 1.20 ms on 48 periodic 1920 x 2560 slices); with a
-  // mask the float64 count plane makes it slower than the rows mode (1.77 vs 1.49 ms), so masked
-  // launches only come here when forced (NBH_SQ_TILE=2)
-  const int mode = env_int("NBH_SQ_TILE", 1);
-  if (mode == 0 || (d.mask2d && mode != 2)) return false;
+  // default for single-member launches (NBH_SQ_TILE=0 selects the rows mode of square_rs_kernel /
+  // the warp kernel): 0.90 vs 1.08 ms on 240 UK slices, 0.76 vs 1.20 ms on 48 periodic 1920 x 2560 slices
+  if (!env_int("NBH_SQ_TILE", 1)) return false;
   const int r = d.cells, nb = 2 * r + 1;
   if (d.n_members != 1 || d.mask_nd || r > 16 || d.nx < 2 * r + 2) return false;
   g->tiles_x = (d.nx + kTileTX - 1) / kTileTX;

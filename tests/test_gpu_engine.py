@@ -318,7 +318,7 @@ def _square_oracle_stack(data, mask, cells, wrap=False, sum_only=False):
                                               ((2, 24, 1480), 4, True), ((4, 51, 700), 9, False)])
 def test_single_member_kernels_match_oracle(shape, cells, wrap, monkeypatch):
     """Single-member slices (the un-fused square path): rows mode of the row-streaming kernel
-    (masked launches), the tile kernel (unmasked launches) and the warp kernel against the oracle with
+    (NBH_SQ_TILE=0), the tile kernel (default) and the warp kernel against the oracle with
     / without an external mask, sum_only, periodic x, wide rows and ones-trimming slices."""
     from improver_b200 import engine
 
@@ -332,7 +332,7 @@ def test_single_member_kernels_match_oracle(shape, cells, wrap, monkeypatch):
         flat[-1, 10:12, -3:] = 0.0
     mask = (rng.random(shape[-2:]) < 0.8).astype(np.uint8)
     variants = {"rows": {"NBH_SQ_TILE": "0", "NBH_SQ_RS_ROWS": "1"},
-                "tile": {"NBH_SQ_TILE": "2", "NBH_SQ_RS_ROWS": "1"},
+                "tile": {"NBH_SQ_TILE": "1", "NBH_SQ_RS_ROWS": "1"},
                 "warp": {"NBH_SQ_TILE": "0", "NBH_SQ_RS_ROWS": "0"}}
     for m in (None, mask):
         md = _dev(m) if m is not None else None
