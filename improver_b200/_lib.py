@@ -77,6 +77,15 @@ def load() -> C.CDLL:
     lib.nbh_vicinity_f32.restype = C.c_int
     lib.nbh_vicinity_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
                                      C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.nbh_recursive_filter_f32.restype = C.c_int
+    lib.nbh_recursive_filter_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                             C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.nbh_recursive_filter_workspace_bytes.restype = C.c_size_t
+    lib.nbh_recursive_filter_workspace_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.nbh_recurse_f32.restype = C.c_int
+    lib.nbh_recurse_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_void_p]
     lib.nbh_profile_enable.argtypes = [C.c_int]
     lib.nbh_profile_last_ms.argtypes = [C.POINTER(C.c_float)]
     lib.nbh_profile_last_kernel.restype = C.c_char_p
@@ -96,4 +105,5 @@ def check(rc: int) -> None:
 EXPORTED = ["nbh_version", "nbh_last_error", "nbh_device_info", "nbh_workspace_bytes",
             "nbh_square_f32", "nbh_circular_f32", "nbh_percentiles_f32",
             "nbh_percentiles_workspace_bytes", "nbh_threshold_f32", "nbh_threshold_vicinity_f32", "nbh_vicinity_f32",
+            "nbh_recursive_filter_f32", "nbh_recursive_filter_workspace_bytes", "nbh_recurse_f32",
             "nbh_profile_enable", "nbh_profile_last_ms", "nbh_profile_last_kernel"]

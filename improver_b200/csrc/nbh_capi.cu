@@ -255,4 +255,23 @@ int nbh_vicinity_f32(const float* in, const uint8_t* mask_nd, const uint8_t* lan
                                      1, n_planes, ny, nx, status, static_cast<cudaStream_t>(stream), op);
 }
 
+int nbh_recursive_filter_f32(const float* in, const float* coeff_x, const float* coeff_y, const uint8_t* mask,
+                             int32_t mask_per_slice, int32_t mask_zeros, float* out, int64_t n_slices,
+                             int32_t ny, int32_t nx, int32_t pad, int32_t iterations, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  return nbh::run_recursive_filter(in, coeff_x, coeff_y, mask, mask_per_slice, mask_zeros, out, n_slices, ny, nx,
+                                   pad, iterations, workspace, workspace_bytes,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+size_t nbh_recursive_filter_workspace_bytes(int64_t n_slices, int32_t ny, int32_t nx, int32_t pad,
+                                            int32_t coeff_per_slice) {
+  return nbh::recursive_filter_workspace_bytes(n_slices, ny, nx, pad, coeff_per_slice);
+}
+
+int nbh_recurse_f32(float* grid, const float* coeffs, int64_t n_slices, int32_t ny, int32_t nx, int32_t axis,
+                    int32_t dirs, void* stream) {
+  return nbh::run_recurse(grid, coeffs, n_slices, ny, nx, axis, dirs, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -202,6 +202,13 @@ template <> struct VecLoad<4> {
 };
 
 // bench.py measurement aid: events around the dominant kernel of a call
+size_t recursive_filter_workspace_bytes(long long n_slices, int ny, int nx, int pad, int coeff_per_slice);
+int run_recursive_filter(const float* in, const float* cx, const float* cy, const uint8_t* mask, int mask_per_slice,
+                         int mask_zeros, float* out, long long n_slices, int ny, int nx, int pad, int iterations,
+                         void* ws, size_t ws_bytes, cudaStream_t st);
+int run_recurse(float* grid, const float* coeffs, long long n_slices, int ny, int nx, int axis, int dirs,
+                cudaStream_t st);
+
 struct ProfileScope {
   cudaStream_t st;
   bool on;

@@ -304,6 +304,73 @@ def extreme_within_vicinity(data: torch.Tensor, vicinity_cells: Sequence[int], o
     return out, status
 
 
+def recursive_filter(data: torch.Tensor, coeff_x: torch.Tensor, coeff_y: torch.Tensor, iterations: int,
+                     edge_width: int = 15, mask: Optional[torch.Tensor] = None, mask_zeros: bool = False):
+    """The per-slice body of RecursiveFilter.process (recursive_filter.py:403-436) for every
+    (y, x) slice of `data` float32 CUDA (..., ny, nx): symmetric halo of 2 * edge_width,
+    `iterations` x (x forward, x backward, y forward, y backward), halo removed.  coeff_x
+    (ny, nx - 1), coeff_y (ny - 1, nx) float32.  `mask` (non-zero = masked) is either one
+    (ny, nx) plane or has the shape of `data`; coefficients next to masked points are zeroed."""
+    lib = _lib.load()
+    for t, name in ((data, "data"), (coeff_x, "coeff_x"), (coeff_y, "coeff_y")):
+        _require_cuda(t, name)
+        if t.dtype != torch.float32:
+            raise TypeError(f"{name} must be float32")
+    if data.dim() < 2:
+        raise TypeError("data must have (y, x) axes")
+    data = data.contiguous()
+    ny, nx = int(data.shape[-2]), int(data.shape[-1])
+    if tuple(coeff_x.shape) != (ny, nx - 1) or tuple(coeff_y.shape) != (ny - 1, nx):
+        raise ValueError(f"coefficient shapes {tuple(coeff_x.shape)}, {tuple(coeff_y.shape)} do not match "
+                         f"a ({ny}, {nx}) slice")
+    n_slices = int(np.prod(data.shape[:-2])) if data.dim() > 2 else 1
+    per_slice = 0
+    if mask is not None:
+        _require_cuda(mask, "mask")
+        if tuple(mask.shape) == tuple(data.shape) and data.dim() > 2:
+            per_slice = 1
+        elif tuple(mask.shape) != (ny, nx):
+            raise ValueError("mask must be (ny, nx) or have the shape of data")
+        mask = (mask != 0).to(torch.uint8).contiguous()
+    coeff_x, coeff_y = coeff_x.contiguous(), coeff_y.contiguous()
+    out = torch.empty_like(data)
+    pad = 2 * int(edge_width)
+    max_call = 65535
+    with torch.cuda.device(data.device):
+        flat_in, flat_out = data.view(n_slices, ny, nx), out.view(n_slices, ny, nx)
+        flat_mask = mask.view(n_slices, ny, nx) if per_slice else mask
+        for s0 in range(0, n_slices, max_call):
+            n = min(max_call, n_slices - s0)
+            nbytes = lib.nbh_recursive_filter_workspace_bytes(n, ny, nx, pad, 1 if (per_slice or mask_zeros) else 0)
+            ws = _workspace(data.device, nbytes)
+            m = None if flat_mask is None else (flat_mask[s0:s0 + n] if per_slice else flat_mask)
+            _lib.check(lib.nbh_recursive_filter_f32(
+                flat_in[s0:s0 + n].data_ptr(), coeff_x.data_ptr(), coeff_y.data_ptr(),
+                m.data_ptr() if m is not None else None, per_slice, 1 if mask_zeros else 0,
+                flat_out[s0:s0 + n].data_ptr(), n, ny, nx, pad, int(iterations), ws.data_ptr(), ws.numel(),
+                _stream_ptr()))
+    return out
+
+
+def recurse(grid: torch.Tensor, coeffs: torch.Tensor, axis: int, forward: bool = True) -> torch.Tensor:
+    """RecursiveFilter._recurse_forward / _recurse_backward (recursive_filter.py:55-153) in place on
+    float32 CUDA (..., ny, nx); axis counts the spatial axes (0 = y, 1 = x)."""
+    lib = _lib.load()
+    _require_cuda(grid, "grid")
+    _require_cuda(coeffs, "coeffs")
+    if grid.dtype != torch.float32 or coeffs.dtype != torch.float32 or not grid.is_contiguous():
+        raise TypeError("grid and coeffs must be float32, grid contiguous")
+    ny, nx = int(grid.shape[-2]), int(grid.shape[-1])
+    want = (ny - 1, nx) if axis == 0 else (ny, nx - 1)
+    if tuple(coeffs.shape) != want:
+        raise ValueError(f"coefficients must have shape {want}")
+    n_slices = int(np.prod(grid.shape[:-2])) if grid.dim() > 2 else 1
+    with torch.cuda.device(grid.device):
+        _lib.check(lib.nbh_recurse_f32(grid.data_ptr(), coeffs.contiguous().data_ptr(), n_slices, ny, nx, int(axis),
+                                       1 if forward else 2, _stream_ptr()))
+    return grid
+
+
 def neighbourhood_percentiles(data: torch.Tensor, cells: int, percentiles: Sequence[float]):
     """Percentiles of the circular neighbourhood of every point
     (nbhood.py:649-667).  data float32 (..., ny, nx) -> (..., P, ny, nx)."""

@@ -143,6 +143,32 @@ int nbh_vicinity_f32(const float* in, const uint8_t* mask_nd, const uint8_t* lan
                      const int32_t* vicinity_cells, int32_t n_vicinity, int32_t op, int64_t n_planes,
                      int32_t ny, int32_t nx, int32_t* status, void* stream);
 
+/* Recursive filter: replaces RecursiveFilter._run_recursion together with the symmetric halo
+ * (pad_cube_with_halo), the zeroing of coefficients around masked points
+ * (OrographicSmoothingCoefficients.zero_masked) and remove_halo_from_cube, i.e. the per-slice body of
+ * RecursiveFilter.process (improver/nbhood/recursive_filter.py:155-202, 262-286, 403-436).
+ *   in       float32 (n_slices, ny, nx)
+ *   coeff_x  float32 (ny, nx - 1), coeff_y float32 (ny - 1, nx): smoothing coefficients
+ *   mask     uint8 or NULL, non-zero = masked point; one (ny, nx) plane for every slice
+ *            (mask_per_slice = 0) or (n_slices, ny, nx) (mask_per_slice = 1)
+ *   mask_zeros  non-zero: points whose input is exactly 0 are masked as well (:395-396)
+ *   pad      halo width in cells = 2 * edge_width; iterations >= 1
+ *   out      float32 (n_slices, ny, nx)
+ * Every float32 operation is rounded as numpy rounds it, so results are bit-identical. */
+int nbh_recursive_filter_f32(const float* in, const float* coeff_x, const float* coeff_y, const uint8_t* mask,
+                             int32_t mask_per_slice, int32_t mask_zeros, float* out, int64_t n_slices,
+                             int32_t ny, int32_t nx, int32_t pad, int32_t iterations, void* workspace,
+                             size_t workspace_bytes, void* stream);
+size_t nbh_recursive_filter_workspace_bytes(int64_t n_slices, int32_t ny, int32_t nx, int32_t pad,
+                                            int32_t coeff_per_slice);
+
+/* One directional sweep in place: RecursiveFilter._recurse_forward / _recurse_backward
+ * (improver/nbhood/recursive_filter.py:55-153).  grid float32 (n_slices, ny, nx);
+ * axis 0 = y with coeffs (ny - 1, nx), axis 1 = x with coeffs (ny, nx - 1);
+ * dirs 1 = forward, 2 = backward, 3 = forward then backward. */
+int nbh_recurse_f32(float* grid, const float* coeffs, int64_t n_slices, int32_t ny, int32_t nx, int32_t axis,
+                    int32_t dirs, void* stream);
+
 /* Measurement aid (bench.py roofline): when enabled, the dominant kernel of
  * the next nbh_square_f32 / nbh_circular_f32 / nbh_percentiles_f32 call is
  * bracketed by CUDA events on the caller's stream.  nbh_profile_last_ms
