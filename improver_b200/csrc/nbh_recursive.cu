@@ -4,17 +4,22 @@
 //
 // The recurrence is evaluated in the reference's operation order with one float32 rounding
 // per operation (no FMA contraction), so a chain cannot be re-associated into a parallel
-// scan; the parallelism is across the rows (x passes) / columns (y passes) of all slices:
-//   rf_x_kernel  one lane per (slice, row), a warp per 32 rows: tiles of 32 x 32 points are read
-//                and written as coalesced rows and transposed through shared memory, the next
-//                tile is in flight while the current one is evaluated; the first forward
-//                sweep reads the un-padded input through the symmetric reflection (no
-//                separate halo pass)
-//   rf_y_kernel  one thread per (slice, column): walks down, then up, eight rows per step;
-//                warp accesses are coalesced rows; the last iteration's upward walk writes
-//                the un-padded output directly
-// Both are bound by HBM traffic (12 B per point and direction) once a few hundred thousand
-// chains are in flight; a chain step itself is FMUL + FADD = 8 cycles.
+// scan; the parallelism is across the rows (x passes) / columns (y passes) of all slices.
+//
+// Workspace layout: the padded planes (data and the two coefficient planes) are stored as
+// 32 x 32 tiles of 4 KB, [slice][tile row][tile column][32][32].  Both sweep directions then
+// touch whole DRAM pages: an x sweep moves a warp along one tile row (4 KB contiguous per
+// step), a y sweep moves a warp down one tile column (128 B per row, 32 consecutive rows
+// contiguous).  With row-major planes either sweep direction fetched 128 B per DRAM page
+// visit and both kernels stalled at ~3.5 TB/s of DRAM traffic.
+//   rf_x_kernel  one lane per row, a warp per tile row: a tile is read as coalesced rows,
+//                transposed through shared memory so that lane l walks row l, and written
+//                back; the next tile is in flight while the current one is evaluated; the
+//                first forward sweep reads the un-padded input through the symmetric
+//                reflection (no separate halo pass)
+//   rf_y_kernel  one thread per (slice, column): walks down, then up, a batch of rows per
+//                step; the last iteration's upward walk writes the un-padded output directly
+// A chain step itself is FMUL + FADD = 8 cycles; both kernels are bound by memory traffic.
 #include "nbh_common.cuh"
 
 namespace nbh {
@@ -36,6 +41,11 @@ __device__ __forceinline__ float rf_step(float c, float a, float b) {
   return __fadd_rn(__fmul_rn(__fsub_rn(1.0f, c), a), __fmul_rn(c, b));
 }
 
+// element (Y, X) of slice s in the tiled plane layout
+__device__ __forceinline__ long long rf_tiled(long long s, int Y, int X, int TY, int TX) {
+  return (((s * TY + (Y >> 5)) * TX + (X >> 5)) << 10) + ((Y & 31) << 5) + (X & 31);
+}
+
 __device__ __forceinline__ bool rf_masked(const float* in, const uint8_t* mask, long long mask_slice_stride,
                                           int mask_zeros, long long s, long long plane, int y, int x, int nx) {
   const long long o = (long long)y * nx + x;
@@ -50,7 +60,8 @@ __device__ __forceinline__ bool rf_masked(const float* in, const uint8_t* mask, 
 __global__ void rf_pad_coeff_kernel(const float* __restrict__ in, const float* __restrict__ cx,
                                     const float* __restrict__ cy, const uint8_t* __restrict__ mask,
                                     long long mask_slice_stride, int mask_zeros, float* __restrict__ cxp,
-                                    float* __restrict__ cyp, int ny, int nx, int pad, int NY, int NX, int PX) {
+                                    float* __restrict__ cyp, int ny, int nx, int pad, int NY, int NX, int TY,
+                                    int TX) {
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
   const int Y = blockIdx.y;
   const long long s = blockIdx.z;
@@ -63,7 +74,9 @@ __global__ void rf_pad_coeff_kernel(const float* __restrict__ in, const float* _
     if (any_mask && (rf_masked(in, mask, mask_slice_stride, mask_zeros, s, plane, y, j, nx) ||
                      rf_masked(in, mask, mask_slice_stride, mask_zeros, s, plane, y, j + 1, nx)))
       c = 0.0f;
-    cxp[(s * NY + Y) * (long long)PX + X] = c;
+    // x-coefficient tiles are stored transposed ([column][row]): the x sweep's lane = row reads
+    // the coefficient of column j as one coalesced row of the tile, no shared-memory transpose
+    cxp[(((s * TY + (Y >> 5)) * TX + (X >> 5)) << 10) + ((X & 31) << 5) + (Y & 31)] = c;
   }
   if (Y < NY - 1) {
     const int i = reflect_symmetric(Y - pad, ny - 1), x = reflect_symmetric(X - pad, nx);
@@ -71,95 +84,104 @@ __global__ void rf_pad_coeff_kernel(const float* __restrict__ in, const float* _
     if (any_mask && (rf_masked(in, mask, mask_slice_stride, mask_zeros, s, plane, i, x, nx) ||
                      rf_masked(in, mask, mask_slice_stride, mask_zeros, s, plane, i + 1, x, nx)))
       c = 0.0f;
-    cyp[(s * NY + Y) * (long long)PX + X] = c;
+    cyp[rf_tiled(s, Y, X, TY, TX)] = c;
   }
 }
 
 
-// x passes.  A warp owns 32 consecutive rows of the flattened (slice, row) list and moves
-// along them in tiles of 32 columns: the tile is read row by row (coalesced 128-byte
-// requests), transposed through shared memory so that lane l walks row l, and written back
-// row by row; the next tile is in flight (registers) while the current one is evaluated.
-// dirs bit 0 = forward, bit 1 = backward.  FROM_SRC: the forward sweep reads the un-padded
-// input through the symmetric reflection instead of the padded plane (fuses the halo
-// construction of pad_cube_with_halo into the first sweep).
-template <bool FROM_SRC, int kRfTile, int kRfXWarps>
+constexpr int kRfTile = 32;
+constexpr int kRfTilePitch = kRfTile + 1;
+constexpr int kRfXWarps = 4;
+
+// x passes.  A warp owns 32 rows and moves along them in tiles of 32 columns: the tile is read
+// row by row (coalesced 128-byte requests), transposed through shared memory so that lane l
+// walks row l, and written back row by row; the next tile is in flight (registers) while the
+// current one is evaluated.  dirs bit 0 = forward, bit 1 = backward.
+//   TILED     planes in the tiled workspace layout, warp = (slice, tile row); otherwise row-major
+//             planes with the given pitches, warp = 32 consecutive rows of the flattened row list
+//   FROM_SRC  the forward sweep reads the un-padded input through the symmetric reflection
+//             instead of the padded plane (fuses pad_cube_with_halo into the first sweep)
+template <bool FROM_SRC, bool TILED>
 __global__ void __launch_bounds__(kRfXWarps * 32)
 rf_x_kernel(float* __restrict__ g, const float* __restrict__ src, const float* __restrict__ cxp,
-            long long n_rows_total, int NY, int NX, long long g_pitch, long long c_pitch, int coeff_per_slice,
-            int dirs, int pad, int ny, int nx) {
-  constexpr int kRfTilePitch = kRfTile + 1, kSub = kRfTile / 32;
+            long long n_units, long long n_rows_total, int NY, int NX, long long g_pitch, long long c_pitch,
+            int coeff_per_slice, int dirs, int pad, int ny, int nx, int TY, int TX) {
   __shared__ float sg_all[kRfXWarps][32 * kRfTilePitch];
-  __shared__ float sc_all[kRfXWarps][32 * kRfTilePitch];
-  __shared__ long long off_all[kRfXWarps][3][32];
+  __shared__ float sc_all[kRfXWarps][TILED ? 1 : 32 * kRfTilePitch];
+  __shared__ long long off_all[kRfXWarps][TILED ? 1 : 2][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sg = sg_all[warp];
   float* sc = sc_all[warp];
-  long long* goff = off_all[warp][0];
-  long long* coff = off_all[warp][1];
-  long long* soff = off_all[warp][2];
-  const long long row0 = (blockIdx.x * (long long)kRfXWarps + warp) * 32;
-  if (row0 >= n_rows_total) return;
-  const int n_rows = (int)min(32LL, n_rows_total - row0);
-  {
-    const long long R = row0 + lane;
+  long long* off0 = off_all[warp][0];                      // TILED: source rows; else data rows
+  long long* off1 = off_all[warp][TILED ? 0 : 1];          // row-major coefficient rows
+  const long long unit = blockIdx.x * (long long)kRfXWarps + warp;
+  if (unit >= n_units) return;
+  int n_rows;
+  long long gbase = 0, cbase = 0;      // TILED: first tile of this warp's tile row
+  if (TILED) {
+    const long long s = unit / TY;
+    const int ty = (int)(unit - s * TY);
+    n_rows = min(32, NY - 32 * ty);
+    gbase = ((s * TY + ty) * TX) << 10;
+    cbase = (((coeff_per_slice ? s : 0) * TY + ty) * TX) << 10;
+    if (FROM_SRC) off0[lane] = (s * ny + reflect_symmetric(32 * ty + lane - pad, ny)) * (long long)nx;
+  } else {
+    const long long R = unit * 32 + lane;
+    n_rows = (int)min(32LL, n_rows_total - unit * 32);
     const long long s = R / NY;
     const int Y = (int)(R - s * NY);
-    goff[lane] = R * g_pitch;
-    coff[lane] = ((coeff_per_slice ? s : 0) * NY + Y) * c_pitch;
-    soff[lane] = FROM_SRC ? (s * ny + reflect_symmetric(Y - pad, ny)) * (long long)nx : 0;
+    off0[lane] = R * g_pitch;
+    off1[lane] = ((coeff_per_slice ? s : 0) * NY + Y) * c_pitch;
   }
   __syncwarp();
   const int nt = (NX + kRfTile - 1) / kRfTile;
-  float pg[32 * kSub], pc[32 * kSub];
+  float pg[32], pc[32];
 
-  // `whole`: all 32 rows exist and the tile lies inside the row, so no element needs a bounds test
   auto fetch = [&](int t, bool from_src) {
-    const bool whole = n_rows == 32 && (t + 1) * kRfTile <= NX - 1;
+    const int X = t * kRfTile + lane;
+    if (TILED) {
+      const float* ct = cxp + cbase + ((long long)t << 10) + lane;   // transposed tile: [column][row]
 #pragma unroll
-    for (int q = 0; q < kSub; ++q) {
-      const int X = t * kRfTile + q * 32 + lane;
-      const int xs = (FROM_SRC && from_src) ? reflect_symmetric(X - pad, nx) : 0;
-      if (whole) {
+      for (int j = 0; j < 32; ++j) pc[j] = ct[j * 32];
+      if (FROM_SRC && from_src) {
+        const int xs = reflect_symmetric(min(X, NX - 1) - pad, nx);
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
-          if (FROM_SRC && from_src) pg[rr * kSub + q] = src[soff[rr] + xs];
-          else pg[rr * kSub + q] = g[goff[rr] + X];
-          pc[rr * kSub + q] = cxp[coff[rr] + X];
-        }
+        for (int rr = 0; rr < 32; ++rr) pg[rr] = src[off0[rr] + xs];
       } else {
-        const bool gok = X < NX, cok = X < NX - 1;
+        const float* gt = g + gbase + ((long long)t << 10) + lane;
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
-          const bool rok = rr < n_rows;
-          if (FROM_SRC && from_src) pg[rr * kSub + q] = (gok && rok) ? src[soff[rr] + xs] : 0.f;
-          else pg[rr * kSub + q] = (gok && rok) ? g[goff[rr] + X] : 0.f;
-          pc[rr * kSub + q] = (cok && rok) ? cxp[coff[rr] + X] : 0.f;
-        }
+        for (int rr = 0; rr < 32; ++rr) pg[rr] = gt[rr * 32];
+      }
+    } else {
+      const bool gok = X < NX, cok = X < NX - 1;
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) {
+        const bool rok = rr < n_rows;
+        pg[rr] = (gok && rok) ? g[off0[rr] + X] : 0.f;
+        pc[rr] = (cok && rok) ? cxp[off1[rr] + X] : 0.f;
       }
     }
   };
+  float cc[32];   // TILED: this lane's coefficients of the staged tile
   auto stage = [&]() {
 #pragma unroll
-    for (int rr = 0; rr < 32; ++rr)
-#pragma unroll
-      for (int q = 0; q < kSub; ++q) {
-        sg[rr * kRfTilePitch + q * 32 + lane] = pg[rr * kSub + q];
-        sc[rr * kRfTilePitch + q * 32 + lane] = pc[rr * kSub + q];
-      }
+    for (int rr = 0; rr < 32; ++rr) {
+      sg[rr * kRfTilePitch + lane] = pg[rr];
+      if (TILED) cc[rr] = pc[rr];
+      else sc[rr * kRfTilePitch + lane] = pc[rr];
+    }
   };
   auto flush = [&](int t) {
-    const bool whole = n_rows == 32 && (t + 1) * kRfTile <= NX;
+    if (TILED) {   // whole tiles: the slack of edge tiles belongs to the workspace
+      float* gt = g + gbase + ((long long)t << 10) + lane;
 #pragma unroll
-    for (int q = 0; q < kSub; ++q) {
-      const int X = t * kRfTile + q * 32 + lane;
-      if (whole) {
-#pragma unroll
-        for (int rr = 0; rr < 32; ++rr) g[goff[rr] + X] = sg[rr * kRfTilePitch + q * 32 + lane];
-      } else if (X < NX) {
+      for (int rr = 0; rr < 32; ++rr) gt[rr * 32] = sg[rr * kRfTilePitch + lane];
+    } else {
+      const int X = t * kRfTile + lane;
+      if (X < NX) {
 #pragma unroll
         for (int rr = 0; rr < 32; ++rr)
-          if (rr < n_rows) g[goff[rr] + X] = sg[rr * kRfTilePitch + q * 32 + lane];
+          if (rr < n_rows) g[off0[rr] + X] = sg[rr * kRfTilePitch + lane];
       }
     }
   };
@@ -176,7 +198,7 @@ rf_x_kernel(float* __restrict__ g, const float* __restrict__ src, const float* _
       if (t > 0 && x0 + kRfTile <= NX) {
 #pragma unroll
         for (int j = 0; j < kRfTile; ++j) {
-          const float c = sc[lane * kRfTilePitch + j];
+          const float c = TILED ? cc[j] : sc[lane * kRfTilePitch + j];
           gprev = rf_step(cprev, sg[lane * kRfTilePitch + j], gprev);
           cprev = c;
           sg[lane * kRfTilePitch + j] = gprev;
@@ -186,7 +208,7 @@ rf_x_kernel(float* __restrict__ g, const float* __restrict__ src, const float* _
         for (int j = 0; j < kRfTile; ++j) {
           const int i = x0 + j;
           float a = sg[lane * kRfTilePitch + j];
-          const float c = sc[lane * kRfTilePitch + j];
+          const float c = TILED ? cc[j] : sc[lane * kRfTilePitch + j];
           if (i >= 1 && i < NX) a = rf_step(cprev, a, gprev);
           gprev = a;
           cprev = c;
@@ -210,7 +232,7 @@ rf_x_kernel(float* __restrict__ g, const float* __restrict__ src, const float* _
       if (x0 + kRfTile <= NX - 1) {
 #pragma unroll
         for (int j = kRfTile - 1; j >= 0; --j) {
-          gnext = rf_step(sc[lane * kRfTilePitch + j], sg[lane * kRfTilePitch + j], gnext);
+          gnext = rf_step(TILED ? cc[j] : sc[lane * kRfTilePitch + j], sg[lane * kRfTilePitch + j], gnext);
           sg[lane * kRfTilePitch + j] = gnext;
         }
       } else {
@@ -218,7 +240,7 @@ rf_x_kernel(float* __restrict__ g, const float* __restrict__ src, const float* _
         for (int j = kRfTile - 1; j >= 0; --j) {
           const int i = x0 + j;
           float a = sg[lane * kRfTilePitch + j];
-          const float c = sc[lane * kRfTilePitch + j];
+          const float c = TILED ? cc[j] : sc[lane * kRfTilePitch + j];
           if (i <= NX - 2) a = rf_step(c, a, gnext);
           gnext = a;
           sg[lane * kRfTilePitch + j] = a;
@@ -231,61 +253,80 @@ rf_x_kernel(float* __restrict__ g, const float* __restrict__ src, const float* _
   }
 }
 
-// One directional walk of a column: `n` steps starting at gp / cp, each pointer advancing by its
-// (possibly negative) stride.  MODE 0 writes the new values in place, 1 writes nothing, 2 writes
-// them to wp.  Full batches issue all their loads before the dependent chain and carry no
-// bounds tests.
-template <int B, int MODE>
-__device__ __forceinline__ float rf_walk(float carry, float* gp, const float* cp, float* wp, int n, long long gs,
-                                         long long cs, long long ws) {
+// Offset of row Y within one column of a plane: tiled workspace layout (stride = floats per
+// tile row) or row-major (stride = pitch).
+template <bool TILED>
+__device__ __forceinline__ long long rf_row(int Y, long long stride) {
+  return TILED ? (long long)(Y >> 5) * stride + ((Y & 31) << 5) : (long long)Y * stride;
+}
+
+// One directional walk of a column: `n` steps from row y_first in direction dir (+1 / -1); the
+// step at row Y uses the coefficient of row Y + c_shift.  MODE 0 writes the new values in place,
+// 1 writes nothing, 2 writes them to wp (advancing by ws per step).  Full batches issue all their
+// loads before the dependent chain.
+template <int B, int MODE, bool TILED>
+__device__ __forceinline__ float rf_walk(float carry, float* gcol, const float* ccol, float* wp, int y_first,
+                                         int dir, int c_shift, int n, long long gs, long long cs, long long ws) {
   int k = 0;
 #pragma unroll 1
   for (; k + B <= n; k += B) {
     float a[B], c[B];
+    long long o[B];
 #pragma unroll
     for (int u = 0; u < B; ++u) {
-      a[u] = gp[u * gs];
-      c[u] = cp[u * cs];
+      const int Y = y_first + dir * (k + u);
+      o[u] = rf_row<TILED>(Y, gs);
+      a[u] = gcol[o[u]];
+      c[u] = ccol[rf_row<TILED>(Y + c_shift, cs)];
     }
 #pragma unroll
     for (int u = 0; u < B; ++u) {
       carry = rf_step(c[u], a[u], carry);
-      if (MODE == 0) gp[u * gs] = carry;
+      if (MODE == 0) gcol[o[u]] = carry;
       if (MODE == 2) wp[u * ws] = carry;
     }
-    gp += B * gs;
-    cp += B * cs;
     if (MODE == 2) wp += B * ws;
   }
 #pragma unroll 1
   for (; k < n; ++k) {
-    carry = rf_step(*cp, *gp, carry);
-    if (MODE == 0) *gp = carry;
+    const int Y = y_first + dir * k;
+    const long long o = rf_row<TILED>(Y, gs);
+    carry = rf_step(ccol[rf_row<TILED>(Y + c_shift, cs)], gcol[o], carry);
+    if (MODE == 0) gcol[o] = carry;
     if (MODE == 2) { *wp = carry; wp += ws; }
-    gp += gs;
-    cp += cs;
   }
   return carry;
 }
 
 // y passes: one thread per (slice, column).  When `out` is set (last iteration) the upward walk
 // writes the interior of the slice to the un-padded output instead of the padded plane.
-template <int kRfBatch>
+template <int kRfBatch, bool TILED>
 __global__ void __launch_bounds__(512)
 rf_y_kernel(float* __restrict__ g, const float* __restrict__ cyp, float* __restrict__ out, int NY, int NX,
-            long long g_pitch, long long c_pitch, int coeff_per_slice, int dirs, int pad, int ny, int nx) {
+            long long g_pitch, long long c_pitch, int coeff_per_slice, int dirs, int pad, int ny, int nx, int TY,
+            int TX) {
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
   const long long s = blockIdx.y;
   if (X >= NX) return;
-  float* gp = g + s * NY * g_pitch + X;
-  const float* cp = cyp + (coeff_per_slice ? s : 0) * NY * c_pitch + X;
-  if (dirs & 1) rf_walk<kRfBatch, 0>(gp[0], gp + g_pitch, cp, nullptr, NY - 1, g_pitch, c_pitch, 0);
+  float* gp;
+  const float* cp;
+  long long gs, cs;
+  if (TILED) {
+    const long long col = ((long long)(X >> 5) << 10) + (X & 31);
+    gs = cs = (long long)TX << 10;
+    gp = g + s * TY * gs + col;
+    cp = cyp + (coeff_per_slice ? s : 0) * TY * cs + col;
+  } else {
+    gs = g_pitch;
+    cs = c_pitch;
+    gp = g + s * NY * g_pitch + X;
+    cp = cyp + (coeff_per_slice ? s : 0) * NY * c_pitch + X;
+  }
+  if (dirs & 1) rf_walk<kRfBatch, 0, TILED>(gp[0], gp, cp, nullptr, 1, 1, -1, NY - 1, gs, cs, 0);
   if (dirs & 2) {
-    float* last = gp + (long long)(NY - 2) * g_pitch;
-    const float* clast = cp + (long long)(NY - 2) * c_pitch;
-    float carry = last[g_pitch];
+    float carry = gp[rf_row<TILED>(NY - 1, gs)];
     if (out == nullptr) {
-      rf_walk<kRfBatch, 0>(carry, last, clast, nullptr, NY - 1, -g_pitch, -c_pitch, 0);
+      rf_walk<kRfBatch, 0, TILED>(carry, gp, cp, nullptr, NY - 2, -1, 0, NY - 1, gs, cs, 0);
       return;
     }
     if (X < pad || X >= pad + nx) return;
@@ -293,19 +334,18 @@ rf_y_kernel(float* __restrict__ g, const float* __restrict__ cyp, float* __restr
     if (pad == 0) op[(long long)(ny - 1) * nx] = carry;
     const int top = min(NY - 2, pad + ny - 1);        // first row of the walk that is part of the output
     const int skip = NY - 2 - top;                    // halo rows below it: evaluated, not stored
-    carry = rf_walk<kRfBatch, 1>(carry, last, clast, nullptr, skip, -g_pitch, -c_pitch, 0);
-    rf_walk<kRfBatch, 2>(carry, last - skip * g_pitch, clast - skip * c_pitch, op + (long long)(top - pad) * nx,
-                         top - pad + 1, -g_pitch, -c_pitch, -(long long)nx);
+    carry = rf_walk<kRfBatch, 1, TILED>(carry, gp, cp, nullptr, NY - 2, -1, 0, skip, gs, cs, 0);
+    rf_walk<kRfBatch, 2, TILED>(carry, gp, cp, op + (long long)(top - pad) * nx, top, -1, 0, top - pad + 1, gs, cs,
+                                -(long long)nx);
   }
 }
 
-inline long long rf_pitch(int NX) { return ((NX + 7) / 8) * 8; }
+inline long long rf_tiles(int n) { return (n + 31) / 32; }
 
 }  // namespace
 
 size_t recursive_filter_workspace_bytes(long long n_slices, int ny, int nx, int pad, int coeff_per_slice) {
-  const long long NY = ny + 2LL * pad, PX = rf_pitch(nx + 2 * pad);
-  const long long plane = NY * PX * 4;
+  const long long plane = rf_tiles(ny + 2 * pad) * rf_tiles(nx + 2 * pad) * 4096;
   return (size_t)(n_slices * plane + 2 * (coeff_per_slice ? n_slices : 1) * plane + 512);
 }
 
@@ -321,45 +361,34 @@ int run_recursive_filter(const float* in, const float* cx, const float* cy, cons
   NBH_REQUIRE(ws && ws_bytes >= recursive_filter_workspace_bytes(n_slices, ny, nx, pad, per_slice),
               "workspace too small for the recursive filter");
   const int NY = ny + 2 * pad, NX = nx + 2 * pad;
-  const long long PX = rf_pitch(NX);
+  const int TY = (int)rf_tiles(NY), TX = (int)rf_tiles(NX);
+  const long long plane = (long long)TY * TX * 1024;
   NBH_REQUIRE(NY <= 65535, "padded slice too tall");
   ProfileScope prof(st, "nbh::rf_x_kernel + nbh::rf_y_kernel (recursive filter)");
   uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
   float* g = reinterpret_cast<float*>(base);
-  float* cxp = g + n_slices * NY * PX;
-  float* cyp = cxp + (per_slice ? n_slices : 1) * NY * PX;
   const long long n_cp = per_slice ? n_slices : 1;
+  float* cxp = g + n_slices * plane;
+  float* cyp = cxp + n_cp * plane;
   dim3 cgrid((NX + 255) / 256, NY, (unsigned)n_cp);
   rf_pad_coeff_kernel<<<cgrid, 256, 0, st>>>(in, cx, cy, mask, mask_per_slice ? (long long)ny * nx : 0LL,
-                                              mask_zeros, cxp, cyp, ny, nx, pad, NY, NX, (int)PX);
-  const long long n_rows = n_slices * NY;
-  const int xtile = env_int("NBH_RF_XTILE", 32);
+                                              mask_zeros, cxp, cyp, ny, nx, pad, NY, NX, TY, TX);
+  const long long n_units = n_slices * TY;
+  const unsigned xb = (unsigned)((n_units + kRfXWarps - 1) / kRfXWarps);
   const int ythreads = env_int("NBH_RF_YTHREADS", 128), ybatch = env_int("NBH_RF_YBATCH", 16);
   dim3 ygrid((NX + ythreads - 1) / ythreads, (unsigned)n_slices);
   for (int it = 0; it < iterations; ++it) {
-    // the first forward sweep builds the symmetric halo on the fly
-    if (xtile == 64) {
-      const unsigned xb = (unsigned)((n_rows + 63) / 64);
-      if (it == 0)
-        rf_x_kernel<true, 64, 2><<<xb, 64, 0, st>>>(g, in, cxp, n_rows, NY, NX, PX, PX, per_slice, 3, pad, ny, nx);
-      else
-        rf_x_kernel<false, 64, 2><<<xb, 64, 0, st>>>(g, nullptr, cxp, n_rows, NY, NX, PX, PX, per_slice, 3, pad, ny,
-                                                     nx);
-    } else {
-      const unsigned xb = (unsigned)((n_rows + 127) / 128);
-      if (it == 0)
-        rf_x_kernel<true, 32, 4><<<xb, 128, 0, st>>>(g, in, cxp, n_rows, NY, NX, PX, PX, per_slice, 3, pad, ny, nx);
-      else
-        rf_x_kernel<false, 32, 4><<<xb, 128, 0, st>>>(g, nullptr, cxp, n_rows, NY, NX, PX, PX, per_slice, 3, pad, ny,
-                                                      nx);
-    }
-    float* o = it == iterations - 1 ? out : nullptr;
-    if (ybatch == 16)
-      rf_y_kernel<16><<<ygrid, ythreads, 0, st>>>(g, cyp, o, NY, NX, PX, PX, per_slice, 3, pad, ny, nx);
-    else if (ybatch == 4)
-      rf_y_kernel<4><<<ygrid, ythreads, 0, st>>>(g, cyp, o, NY, NX, PX, PX, per_slice, 3, pad, ny, nx);
+    if (it == 0)   // the first forward sweep builds the symmetric halo on the fly
+      rf_x_kernel<true, true><<<xb, kRfXWarps * 32, 0, st>>>(g, in, cxp, n_units, 0, NY, NX, 0, 0, per_slice, 3, pad,
+                                                             ny, nx, TY, TX);
     else
-      rf_y_kernel<8><<<ygrid, ythreads, 0, st>>>(g, cyp, o, NY, NX, PX, PX, per_slice, 3, pad, ny, nx);
+      rf_x_kernel<false, true><<<xb, kRfXWarps * 32, 0, st>>>(g, nullptr, cxp, n_units, 0, NY, NX, 0, 0, per_slice,
+                                                              3, pad, ny, nx, TY, TX);
+    float* o = it == iterations - 1 ? out : nullptr;
+    if (ybatch == 8)
+      rf_y_kernel<8, true><<<ygrid, ythreads, 0, st>>>(g, cyp, o, NY, NX, 0, 0, per_slice, 3, pad, ny, nx, TY, TX);
+    else
+      rf_y_kernel<16, true><<<ygrid, ythreads, 0, st>>>(g, cyp, o, NY, NX, 0, 0, per_slice, 3, pad, ny, nx, TY, TX);
   }
   NBH_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -377,13 +406,14 @@ int run_recurse(float* grid, const float* coeffs, long long n_slices, int ny, in
   if (n_slices == 0) return 0;
   if (axis == 1) {
     if (nx < 2) return 0;
-    const long long n_rows = n_slices * ny;
-    rf_x_kernel<false, 32, 4><<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(
-        grid, nullptr, coeffs, n_rows, ny, nx, nx, nx - 1, 0, dirs, 0, ny, nx);
+    const long long n_rows = n_slices * ny, n_units = (n_rows + 31) / 32;
+    rf_x_kernel<false, false><<<(unsigned)((n_units + kRfXWarps - 1) / kRfXWarps), kRfXWarps * 32, 0, st>>>(
+        grid, nullptr, coeffs, n_units, n_rows, ny, nx, nx, nx - 1, 0, dirs, 0, ny, nx, 0, 0);
   } else {
     if (ny < 2) return 0;
     dim3 ygrid((nx + kRfThreads - 1) / kRfThreads, (unsigned)n_slices);
-    rf_y_kernel<8><<<ygrid, kRfThreads, 0, st>>>(grid, coeffs, nullptr, ny, nx, nx, nx, 0, dirs, 0, ny, nx);
+    rf_y_kernel<8, false><<<ygrid, kRfThreads, 0, st>>>(grid, coeffs, nullptr, ny, nx, nx, nx, 0, dirs, 0, ny, nx, 0,
+                                                        0);
   }
   NBH_CHECK_CUDA(cudaGetLastError());
   return 0;
