@@ -89,6 +89,63 @@ __global__ void rf_pad_coeff_kernel(const float* __restrict__ in, const float* _
 }
 
 
+// Per-slice masks: instead of one pair of coefficient planes per slice (8 B per point written and
+// 16 B read per iteration) the sweeps keep the shared planes and read one byte per point that says
+// "this coefficient is zeroed in this slice" (zx transposed like the x coefficients).
+__global__ void __launch_bounds__(256)
+rf_zero_flags_kernel(const float* __restrict__ in, const uint8_t* __restrict__ mask, long long mask_slice_stride,
+                     int mask_zeros, uint8_t* __restrict__ zx, uint8_t* __restrict__ zy, int ny, int nx, int pad,
+                     int NY, int NX, int TY, int TX) {
+  // one block of 32 x 8 threads per 32 x 32 tile; threadIdx.x is the fast index of the tile being written
+  const long long s = blockIdx.z;
+  const long long tile = ((s * TY + blockIdx.y) * TX + blockIdx.x) << 10;
+  const long long plane = (long long)ny * nx;
+  const int y0 = blockIdx.y * 32 - pad, x0 = blockIdx.x * 32 - pad;   // data coordinates of the tile origin
+  const int tx = threadIdx.x;
+  if (y0 >= 0 && y0 + 32 <= ny - 1 && x0 >= 0 && x0 + 32 <= nx - 1) {
+    // tile away from the halo: no reflection; stage the 33 x 33 patch of "masked" bits once
+    __shared__ uint8_t sm[33][36];
+    const int tid = threadIdx.y * 32 + tx;
+    bool v[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const int idx = tid + q * 256, r = idx / 33, c = idx - r * 33;
+      v[q] = idx < 33 * 33 && rf_masked(in, mask, mask_slice_stride, mask_zeros, s, plane, y0 + r, x0 + c, nx);
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const int idx = tid + q * 256, r = idx / 33, c = idx - r * 33;
+      if (idx < 33 * 33) sm[r][c] = v[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ty = threadIdx.y + 8 * q;
+      zy[tile + (ty << 5) + tx] = sm[ty][tx] | sm[ty + 1][tx];
+      zx[tile + (ty << 5) + tx] = sm[tx][ty] | sm[tx][ty + 1];
+    }
+    return;
+  }
+  for (int ty = threadIdx.y; ty < 32; ty += 8) {
+    {
+      const int X = blockIdx.x * 32 + tx, Y = blockIdx.y * 32 + ty;
+      if (X < NX && Y < NY - 1) {
+        const int i = reflect_symmetric(Y - pad, ny - 1), x = reflect_symmetric(X - pad, nx);
+        zy[tile + (ty << 5) + tx] = rf_masked(in, mask, mask_slice_stride, mask_zeros, s, plane, i, x, nx) ||
+                                    rf_masked(in, mask, mask_slice_stride, mask_zeros, s, plane, i + 1, x, nx);
+      }
+    }
+    {
+      const int X = blockIdx.x * 32 + ty, Y = blockIdx.y * 32 + tx;   // transposed tile
+      if (X < NX - 1 && Y < NY) {
+        const int y = reflect_symmetric(Y - pad, ny), j = reflect_symmetric(X - pad, nx - 1);
+        zx[tile + (ty << 5) + tx] = rf_masked(in, mask, mask_slice_stride, mask_zeros, s, plane, y, j, nx) ||
+                                    rf_masked(in, mask, mask_slice_stride, mask_zeros, s, plane, y, j + 1, nx);
+      }
+    }
+  }
+}
+
 constexpr int kRfTile = 32;
 constexpr int kRfTilePitch = kRfTile + 1;
 constexpr int kRfXWarps = 4;
@@ -105,7 +162,8 @@ template <bool FROM_SRC, bool TILED>
 __global__ void __launch_bounds__(kRfXWarps * 32)
 rf_x_kernel(float* __restrict__ g, const float* __restrict__ src, const float* __restrict__ cxp,
             long long n_units, long long n_rows_total, int NY, int NX, long long g_pitch, long long c_pitch,
-            int coeff_per_slice, int dirs, int pad, int ny, int nx, int TY, int TX) {
+            int coeff_per_slice, int dirs, int pad, int ny, int nx, int TY, int TX,
+            const uint8_t* __restrict__ zx) {
   __shared__ float sg_all[kRfXWarps][32 * kRfTilePitch];
   __shared__ float sc_all[kRfXWarps][TILED ? 1 : 32 * kRfTilePitch];
   __shared__ long long off_all[kRfXWarps][TILED ? 1 : 2][32];
@@ -141,8 +199,14 @@ rf_x_kernel(float* __restrict__ g, const float* __restrict__ src, const float* _
     const int X = t * kRfTile + lane;
     if (TILED) {
       const float* ct = cxp + cbase + ((long long)t << 10) + lane;   // transposed tile: [column][row]
+      if (zx) {
+        const uint8_t* zt = zx + gbase + ((long long)t << 10) + lane;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) pc[j] = ct[j * 32];
+        for (int j = 0; j < 32; ++j) pc[j] = zt[j * 32] ? 0.f : ct[j * 32];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pc[j] = ct[j * 32];
+      }
       if (FROM_SRC && from_src) {
         const int xs = reflect_symmetric(min(X, NX - 1) - pad, nx);
 #pragma unroll
@@ -264,9 +328,10 @@ __device__ __forceinline__ long long rf_row(int Y, long long stride) {
 // step at row Y uses the coefficient of row Y + c_shift.  MODE 0 writes the new values in place,
 // 1 writes nothing, 2 writes them to wp (advancing by ws per step).  Full batches issue all their
 // loads before the dependent chain.
-template <int B, int MODE, bool TILED>
-__device__ __forceinline__ float rf_walk(float carry, float* gcol, const float* ccol, float* wp, int y_first,
-                                         int dir, int c_shift, int n, long long gs, long long cs, long long ws) {
+template <int B, int MODE, bool TILED, bool Z>
+__device__ __forceinline__ float rf_walk(float carry, float* gcol, const float* ccol, const uint8_t* zcol, float* wp,
+                                         int y_first, int dir, int c_shift, int n, long long gs, long long cs,
+                                         long long ws) {
   int k = 0;
 #pragma unroll 1
   for (; k + B <= n; k += B) {
@@ -277,7 +342,9 @@ __device__ __forceinline__ float rf_walk(float carry, float* gcol, const float* 
       const int Y = y_first + dir * (k + u);
       o[u] = rf_row<TILED>(Y, gs);
       a[u] = gcol[o[u]];
-      c[u] = ccol[rf_row<TILED>(Y + c_shift, cs)];
+      const long long oc = rf_row<TILED>(Y + c_shift, cs);
+      c[u] = ccol[oc];
+      if (Z && zcol[oc]) c[u] = 0.f;
     }
 #pragma unroll
     for (int u = 0; u < B; ++u) {
@@ -291,7 +358,10 @@ __device__ __forceinline__ float rf_walk(float carry, float* gcol, const float* 
   for (; k < n; ++k) {
     const int Y = y_first + dir * k;
     const long long o = rf_row<TILED>(Y, gs);
-    carry = rf_step(ccol[rf_row<TILED>(Y + c_shift, cs)], gcol[o], carry);
+    const long long oc = rf_row<TILED>(Y + c_shift, cs);
+    float c1 = ccol[oc];
+    if (Z && zcol[oc]) c1 = 0.f;
+    carry = rf_step(c1, gcol[o], carry);
     if (MODE == 0) gcol[o] = carry;
     if (MODE == 2) { *wp = carry; wp += ws; }
   }
@@ -300,21 +370,23 @@ __device__ __forceinline__ float rf_walk(float carry, float* gcol, const float* 
 
 // y passes: one thread per (slice, column).  When `out` is set (last iteration) the upward walk
 // writes the interior of the slice to the un-padded output instead of the padded plane.
-template <int kRfBatch, bool TILED>
+template <int kRfBatch, bool TILED, bool Z>
 __global__ void __launch_bounds__(512)
 rf_y_kernel(float* __restrict__ g, const float* __restrict__ cyp, float* __restrict__ out, int NY, int NX,
             long long g_pitch, long long c_pitch, int coeff_per_slice, int dirs, int pad, int ny, int nx, int TY,
-            int TX) {
+            int TX, const uint8_t* __restrict__ zy) {
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
   const long long s = blockIdx.y;
   if (X >= NX) return;
   float* gp;
   const float* cp;
+  const uint8_t* zp = nullptr;
   long long gs, cs;
   if (TILED) {
     const long long col = ((long long)(X >> 5) << 10) + (X & 31);
     gs = cs = (long long)TX << 10;
     gp = g + s * TY * gs + col;
+    if (Z) zp = zy + s * TY * gs + col;
     cp = cyp + (coeff_per_slice ? s : 0) * TY * cs + col;
   } else {
     gs = g_pitch;
@@ -322,11 +394,11 @@ rf_y_kernel(float* __restrict__ g, const float* __restrict__ cyp, float* __restr
     gp = g + s * NY * g_pitch + X;
     cp = cyp + (coeff_per_slice ? s : 0) * NY * c_pitch + X;
   }
-  if (dirs & 1) rf_walk<kRfBatch, 0, TILED>(gp[0], gp, cp, nullptr, 1, 1, -1, NY - 1, gs, cs, 0);
+  if (dirs & 1) rf_walk<kRfBatch, 0, TILED, Z>(gp[0], gp, cp, zp, nullptr, 1, 1, -1, NY - 1, gs, cs, 0);
   if (dirs & 2) {
     float carry = gp[rf_row<TILED>(NY - 1, gs)];
     if (out == nullptr) {
-      rf_walk<kRfBatch, 0, TILED>(carry, gp, cp, nullptr, NY - 2, -1, 0, NY - 1, gs, cs, 0);
+      rf_walk<kRfBatch, 0, TILED, Z>(carry, gp, cp, zp, nullptr, NY - 2, -1, 0, NY - 1, gs, cs, 0);
       return;
     }
     if (X < pad || X >= pad + nx) return;
@@ -334,8 +406,8 @@ rf_y_kernel(float* __restrict__ g, const float* __restrict__ cyp, float* __restr
     if (pad == 0) op[(long long)(ny - 1) * nx] = carry;
     const int top = min(NY - 2, pad + ny - 1);        // first row of the walk that is part of the output
     const int skip = NY - 2 - top;                    // halo rows below it: evaluated, not stored
-    carry = rf_walk<kRfBatch, 1, TILED>(carry, gp, cp, nullptr, NY - 2, -1, 0, skip, gs, cs, 0);
-    rf_walk<kRfBatch, 2, TILED>(carry, gp, cp, op + (long long)(top - pad) * nx, top, -1, 0, top - pad + 1, gs, cs,
+    carry = rf_walk<kRfBatch, 1, TILED, Z>(carry, gp, cp, zp, nullptr, NY - 2, -1, 0, skip, gs, cs, 0);
+    rf_walk<kRfBatch, 2, TILED, Z>(carry, gp, cp, zp, op + (long long)(top - pad) * nx, top, -1, 0, top - pad + 1, gs, cs,
                                 -(long long)nx);
   }
 }
@@ -346,7 +418,8 @@ inline long long rf_tiles(int n) { return (n + 31) / 32; }
 
 size_t recursive_filter_workspace_bytes(long long n_slices, int ny, int nx, int pad, int coeff_per_slice) {
   const long long plane = rf_tiles(ny + 2 * pad) * rf_tiles(nx + 2 * pad) * 4096;
-  return (size_t)(n_slices * plane + 2 * (coeff_per_slice ? n_slices : 1) * plane + 512);
+  // data planes, one pair of coefficient planes, and one pair of byte planes per slice for per-slice masks
+  return (size_t)(n_slices * plane + 2 * plane + (coeff_per_slice ? 2 * n_slices * (plane / 4) : 0) + 512);
 }
 
 int run_recursive_filter(const float* in, const float* cx, const float* cy, const uint8_t* mask, int mask_per_slice,
@@ -367,28 +440,36 @@ int run_recursive_filter(const float* in, const float* cx, const float* cy, cons
   ProfileScope prof(st, "nbh::rf_x_kernel + nbh::rf_y_kernel (recursive filter)");
   uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255);
   float* g = reinterpret_cast<float*>(base);
-  const long long n_cp = per_slice ? n_slices : 1;
   float* cxp = g + n_slices * plane;
-  float* cyp = cxp + n_cp * plane;
-  dim3 cgrid((NX + 255) / 256, NY, (unsigned)n_cp);
-  rf_pad_coeff_kernel<<<cgrid, 256, 0, st>>>(in, cx, cy, mask, mask_per_slice ? (long long)ny * nx : 0LL,
-                                              mask_zeros, cxp, cyp, ny, nx, pad, NY, NX, TY, TX);
+  float* cyp = cxp + plane;
+  uint8_t* zx = per_slice ? reinterpret_cast<uint8_t*>(cyp + plane) : nullptr;
+  uint8_t* zy = per_slice ? zx + n_slices * plane : nullptr;
+  // a mask shared by all slices is folded into the coefficient planes; per-slice masks become flags
+  dim3 cgrid((NX + 255) / 256, NY, 1);
+  rf_pad_coeff_kernel<<<cgrid, 256, 0, st>>>(in, cx, cy, per_slice ? nullptr : mask, 0LL, 0, cxp, cyp, ny, nx, pad,
+                                              NY, NX, TY, TX);
+  if (per_slice) {
+    dim3 zgrid(TX, TY, (unsigned)n_slices);
+    rf_zero_flags_kernel<<<zgrid, dim3(32, 8), 0, st>>>(in, mask, mask && mask_per_slice ? (long long)ny * nx : 0LL,
+                                                mask_zeros, zx, zy, ny, nx, pad, NY, NX, TY, TX);
+  }
   const long long n_units = n_slices * TY;
   const unsigned xb = (unsigned)((n_units + kRfXWarps - 1) / kRfXWarps);
-  const int ythreads = env_int("NBH_RF_YTHREADS", 128), ybatch = env_int("NBH_RF_YBATCH", 16);
+  const int ythreads = env_int("NBH_RF_YTHREADS", 128);
   dim3 ygrid((NX + ythreads - 1) / ythreads, (unsigned)n_slices);
   for (int it = 0; it < iterations; ++it) {
     if (it == 0)   // the first forward sweep builds the symmetric halo on the fly
-      rf_x_kernel<true, true><<<xb, kRfXWarps * 32, 0, st>>>(g, in, cxp, n_units, 0, NY, NX, 0, 0, per_slice, 3, pad,
-                                                             ny, nx, TY, TX);
+      rf_x_kernel<true, true><<<xb, kRfXWarps * 32, 0, st>>>(g, in, cxp, n_units, 0, NY, NX, 0, 0, 0, 3, pad, ny, nx,
+                                                             TY, TX, zx);
     else
-      rf_x_kernel<false, true><<<xb, kRfXWarps * 32, 0, st>>>(g, nullptr, cxp, n_units, 0, NY, NX, 0, 0, per_slice,
-                                                              3, pad, ny, nx, TY, TX);
+      rf_x_kernel<false, true><<<xb, kRfXWarps * 32, 0, st>>>(g, nullptr, cxp, n_units, 0, NY, NX, 0, 0, 0, 3, pad,
+                                                              ny, nx, TY, TX, zx);
     float* o = it == iterations - 1 ? out : nullptr;
-    if (ybatch == 8)
-      rf_y_kernel<8, true><<<ygrid, ythreads, 0, st>>>(g, cyp, o, NY, NX, 0, 0, per_slice, 3, pad, ny, nx, TY, TX);
+    if (per_slice)
+      rf_y_kernel<16, true, true><<<ygrid, ythreads, 0, st>>>(g, cyp, o, NY, NX, 0, 0, 0, 3, pad, ny, nx, TY, TX, zy);
     else
-      rf_y_kernel<16, true><<<ygrid, ythreads, 0, st>>>(g, cyp, o, NY, NX, 0, 0, per_slice, 3, pad, ny, nx, TY, TX);
+      rf_y_kernel<16, true, false><<<ygrid, ythreads, 0, st>>>(g, cyp, o, NY, NX, 0, 0, 0, 3, pad, ny, nx, TY, TX,
+                                                               nullptr);
   }
   NBH_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -408,12 +489,12 @@ int run_recurse(float* grid, const float* coeffs, long long n_slices, int ny, in
     if (nx < 2) return 0;
     const long long n_rows = n_slices * ny, n_units = (n_rows + 31) / 32;
     rf_x_kernel<false, false><<<(unsigned)((n_units + kRfXWarps - 1) / kRfXWarps), kRfXWarps * 32, 0, st>>>(
-        grid, nullptr, coeffs, n_units, n_rows, ny, nx, nx, nx - 1, 0, dirs, 0, ny, nx, 0, 0);
+        grid, nullptr, coeffs, n_units, n_rows, ny, nx, nx, nx - 1, 0, dirs, 0, ny, nx, 0, 0, nullptr);
   } else {
     if (ny < 2) return 0;
     dim3 ygrid((nx + kRfThreads - 1) / kRfThreads, (unsigned)n_slices);
-    rf_y_kernel<8, false><<<ygrid, kRfThreads, 0, st>>>(grid, coeffs, nullptr, ny, nx, nx, nx, 0, dirs, 0, ny, nx, 0,
-                                                        0);
+    rf_y_kernel<8, false, false><<<ygrid, kRfThreads, 0, st>>>(grid, coeffs, nullptr, ny, nx, nx, nx, 0, dirs, 0,
+                                                               ny, nx, 0, 0, nullptr);
   }
   NBH_CHECK_CUDA(cudaGetLastError());
   return 0;
