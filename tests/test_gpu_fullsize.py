@@ -124,3 +124,31 @@ def test_percentiles_fullsize_properties():
     exp = orc.neighbourhood_percentiles(host, 10, (5, 25, 50, 75, 95))
     got = out[0, :, 100:160, 200:300].cpu().numpy()
     np.testing.assert_allclose(got[:, 10:-10, 10:-10], exp[:, 10:-10, 10:-10], atol=1e-5)
+
+
+def test_recursive_filter_fullsize_vs_oracle_and_properties():
+    """240 UK slices, edge_width 15: (a) bit-identical to the oracle on a sub-sample of slices
+    (plain and mask_zeros), (b) zero coefficients leave the field untouched, (c) the filter is a
+    convex combination of inputs, so outputs stay inside the range of the slice, and with
+    mask_zeros the exact zeros stay exact zeros."""
+    from improver_b200 import engine
+    from oracle import recursive_filter_oracle as rfo
+
+    g = torch.Generator(device="cuda").manual_seed(9)
+    data = torch.rand((240, NY, NX), generator=g, device="cuda")
+    data[data < 0.3] = 0.0
+    cx = torch.rand((NY, NX - 1), generator=g, device="cuda") * 0.5
+    cy = torch.rand((NY - 1, NX), generator=g, device="cuda") * 0.5
+    hx, hy = cx.cpu().numpy(), cy.cpu().numpy()
+    for mask_zeros in (False, True):
+        out = engine.recursive_filter(data, cx, cy, 1, 15, mask_zeros=mask_zeros)
+        for s in (0, 117, 239):
+            want = rfo.recursive_filter(data[s].cpu().numpy(), hx, hy, 1, 15, mask_zeros=mask_zeros)
+            np.testing.assert_array_equal(out[s].cpu().numpy(), np.ma.getdata(want))
+        lo = data.amin(dim=(-2, -1), keepdim=True)
+        hi = data.amax(dim=(-2, -1), keepdim=True)
+        assert bool(((out >= lo - 1e-6) & (out <= hi + 1e-6)).all())
+        if mask_zeros:
+            assert bool(((out == 0.0) == (data == 0.0)).all())
+    same = engine.recursive_filter(data[:16], torch.zeros_like(cx), torch.zeros_like(cy), 2, 15)
+    assert bool((same == data[:16]).all())
