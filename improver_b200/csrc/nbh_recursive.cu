@@ -158,8 +158,8 @@ constexpr int kRfXWarps = 4;
 //             planes with the given pitches, warp = 32 consecutive rows of the flattened row list
 //   FROM_SRC  the forward sweep reads the un-padded input through the symmetric reflection
 //             instead of the padded plane (fuses pad_cube_with_halo into the first sweep)
-template <bool FROM_SRC, bool TILED>
-__global__ void __launch_bounds__(kRfXWarps * 32)
+template <bool FROM_SRC, bool TILED, int MINB = 4>
+__global__ void __launch_bounds__(kRfXWarps * 32, MINB)
 rf_x_kernel(float* __restrict__ g, const float* __restrict__ src, const float* __restrict__ cxp,
             long long n_units, long long n_rows_total, int NY, int NX, long long g_pitch, long long c_pitch,
             int coeff_per_slice, int dirs, int pad, int ny, int nx, int TY, int TX,
@@ -455,15 +455,24 @@ int run_recursive_filter(const float* in, const float* cx, const float* cy, cons
   }
   const long long n_units = n_slices * TY;
   const unsigned xb = (unsigned)((n_units + kRfXWarps - 1) / kRfXWarps);
-  const int ythreads = env_int("NBH_RF_YTHREADS", 128);
+  const int ythreads = env_int("NBH_RF_YTHREADS", 128), xminb = env_int("NBH_RF_XMINB", 4);
   dim3 ygrid((NX + ythreads - 1) / ythreads, (unsigned)n_slices);
   for (int it = 0; it < iterations; ++it) {
-    if (it == 0)   // the first forward sweep builds the symmetric halo on the fly
+    // the first forward sweep builds the symmetric halo on the fly
+    if (xminb == 5) {
+      if (it == 0)
+        rf_x_kernel<true, true, 5><<<xb, kRfXWarps * 32, 0, st>>>(g, in, cxp, n_units, 0, NY, NX, 0, 0, 0, 3, pad, ny,
+                                                                  nx, TY, TX, zx);
+      else
+        rf_x_kernel<false, true, 5><<<xb, kRfXWarps * 32, 0, st>>>(g, nullptr, cxp, n_units, 0, NY, NX, 0, 0, 0, 3,
+                                                                   pad, ny, nx, TY, TX, zx);
+    } else if (it == 0) {
       rf_x_kernel<true, true><<<xb, kRfXWarps * 32, 0, st>>>(g, in, cxp, n_units, 0, NY, NX, 0, 0, 0, 3, pad, ny, nx,
                                                              TY, TX, zx);
-    else
+    } else {
       rf_x_kernel<false, true><<<xb, kRfXWarps * 32, 0, st>>>(g, nullptr, cxp, n_units, 0, NY, NX, 0, 0, 0, 3, pad,
                                                               ny, nx, TY, TX, zx);
+    }
     float* o = it == iterations - 1 ? out : nullptr;
     if (per_slice)
       rf_y_kernel<16, true, true><<<ygrid, ythreads, 0, st>>>(g, cyp, o, NY, NX, 0, 0, 0, 3, pad, ny, nx, TY, TX, zy);

@@ -7,6 +7,8 @@ all arithmetic happens in libimprover_b200.so through the C ABI
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import Optional, Sequence, Tuple
 
@@ -335,13 +337,20 @@ def recursive_filter(data: torch.Tensor, coeff_x: torch.Tensor, coeff_y: torch.T
     coeff_x, coeff_y = coeff_x.contiguous(), coeff_y.contiguous()
     out = torch.empty_like(data)
     pad = 2 * int(edge_width)
-    max_call = 65535
     with torch.cuda.device(data.device):
+        # slices per launch group: bounded by the grid (65535) and by a workspace budget (padded data
+        # planes + per-slice flag planes) of half the free device memory, at most 16 GiB
+        coeff_flag = 1 if (per_slice or mask_zeros) else 0
+        one = lib.nbh_recursive_filter_workspace_bytes(1, ny, nx, pad, coeff_flag)
+        two = lib.nbh_recursive_filter_workspace_bytes(2, ny, nx, pad, coeff_flag)
+        budget = min(16 << 30, torch.cuda.mem_get_info(data.device)[0] // 2)
+        max_call = int(max(1, min(65535, (budget - one) // max(1, two - one) + 1)))
+        max_call = max(1, min(max_call, int(os.environ.get("NBH_RF_MAX_SLICES", max_call))))
         flat_in, flat_out = data.view(n_slices, ny, nx), out.view(n_slices, ny, nx)
         flat_mask = mask.view(n_slices, ny, nx) if per_slice else mask
         for s0 in range(0, n_slices, max_call):
             n = min(max_call, n_slices - s0)
-            nbytes = lib.nbh_recursive_filter_workspace_bytes(n, ny, nx, pad, 1 if (per_slice or mask_zeros) else 0)
+            nbytes = lib.nbh_recursive_filter_workspace_bytes(n, ny, nx, pad, coeff_flag)
             ws = _workspace(data.device, nbytes)
             m = None if flat_mask is None else (flat_mask[s0:s0 + n] if per_slice else flat_mask)
             _lib.check(lib.nbh_recursive_filter_f32(

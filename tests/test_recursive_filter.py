@@ -321,3 +321,30 @@ def test_run_recursion_known_answers_on_gpu():
             assert abs(result.data[4][4] - check) < 1e-7
         else:
             np.testing.assert_array_almost_equal(result.data[2:-2, 2:-2], KAT_DIFFERENT)
+
+
+@pytest.mark.gpu
+def test_cuda_filter_launch_groups_are_equivalent(monkeypatch):
+    """Slices are independent: splitting a call into launch groups (workspace budget) must not
+    change a bit, with shared and with per-slice masks."""
+    import torch
+
+    from improver_b200 import engine
+
+    rng = np.random.default_rng(21)
+    data = rng.random((7, 45, 52)).astype(np.float32)
+    data[data < 0.3] = 0.0
+    mask = rng.random(data.shape) < 0.2
+    cx = (rng.random((45, 51)) * 0.5).astype(np.float32)
+    cy = (rng.random((44, 52)) * 0.5).astype(np.float32)
+    args = (torch.from_numpy(data).cuda(), torch.from_numpy(cx).cuda(), torch.from_numpy(cy).cuda(), 2, 3)
+    dev_mask = torch.from_numpy(mask.astype(np.uint8)).cuda()
+    whole = [engine.recursive_filter(*args, mask=m, mask_zeros=z).cpu().numpy()
+             for m, z in ((None, False), (dev_mask, False), (None, True))]
+    monkeypatch.setenv("NBH_RF_MAX_SLICES", "3")
+    split = [engine.recursive_filter(*args, mask=m, mask_zeros=z).cpu().numpy()
+             for m, z in ((None, False), (dev_mask, False), (None, True))]
+    for a, b in zip(whole, split):
+        np.testing.assert_array_equal(a, b)
+    want = rfo.recursive_filter(np.ma.masked_array(data, mask), cx, cy, 2, 3)
+    np.testing.assert_array_equal(split[1], np.ma.getdata(want))
