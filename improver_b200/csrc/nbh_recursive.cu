@@ -158,7 +158,8 @@ constexpr int kRfXWarps = 4;
 //             planes with the given pitches, warp = 32 consecutive rows of the flattened row list
 //   FROM_SRC  the forward sweep reads the un-padded input through the symmetric reflection
 //             instead of the padded plane (fuses pad_cube_with_halo into the first sweep)
-// Optional fusion of the y-forward sweep into the x-backward sweep (tile-row wavefront): after a
+// Fusion of the y-forward sweep into the x-backward sweep (tile-row wavefront, NBH_RF_FUSE=0 turns
+// it off): after a
 // warp has finished the x-backward values of tile (ty, t) it continues the y-forward chains of the
 // tile's 32 columns through its 32 rows, starting from row 31 of tile (ty - 1, t), which the warp
 // of the tile row above publishes through a per-(slice, tile row) progress counter.  The
@@ -172,8 +173,8 @@ struct RfFuse {
   long long n_slices;
 };
 
-template <bool FROM_SRC, bool TILED, int MINB = 4>
-__global__ void __launch_bounds__(kRfXWarps * 32, MINB)
+template <bool FROM_SRC, bool TILED>
+__global__ void __launch_bounds__(kRfXWarps * 32, 4)
 rf_x_kernel(float* __restrict__ g, const float* __restrict__ src, const float* __restrict__ cxp,
             long long n_units, long long n_rows_total, int NY, int NX, long long g_pitch, long long c_pitch,
             int coeff_per_slice, int dirs, int pad, int ny, int nx, int TY, int TX,
@@ -508,7 +509,7 @@ int run_recursive_filter(const float* in, const float* cx, const float* cy, cons
   uint8_t* zy = per_slice ? zx + n_slices * plane : nullptr;
   uint8_t* after = per_slice ? zy + n_slices * plane : reinterpret_cast<uint8_t*>(cyp + plane);
   unsigned* progress = reinterpret_cast<unsigned*>((reinterpret_cast<uintptr_t>(after) + 255) & ~uintptr_t(255));
-  const bool fuse_on = env_int("NBH_RF_FUSE", 0) != 0;
+  const bool fuse_on = env_int("NBH_RF_FUSE", 1) != 0;
   RfFuse fuse{fuse_on ? cyp : nullptr, zy, progress, n_slices};
   // a mask shared by all slices is folded into the coefficient planes; per-slice masks become flags
   dim3 cgrid((NX + 255) / 256, NY, 1);
@@ -521,19 +522,12 @@ int run_recursive_filter(const float* in, const float* cx, const float* cy, cons
   }
   const long long n_units = n_slices * TY;
   const unsigned xb = (unsigned)((n_units + kRfXWarps - 1) / kRfXWarps);
-  const int ythreads = env_int("NBH_RF_YTHREADS", 128), xminb = env_int("NBH_RF_XMINB", 4);
+  const int ythreads = env_int("NBH_RF_YTHREADS", 128);
   dim3 ygrid((NX + ythreads - 1) / ythreads, (unsigned)n_slices);
   for (int it = 0; it < iterations; ++it) {
     if (fuse_on) NBH_CHECK_CUDA(cudaMemsetAsync(progress, 0, (size_t)n_slices * TY * 4, st));
     // the first forward sweep builds the symmetric halo on the fly
-    if (xminb == 5) {
-      if (it == 0)
-        rf_x_kernel<true, true, 5><<<xb, kRfXWarps * 32, 0, st>>>(g, in, cxp, n_units, 0, NY, NX, 0, 0, 0, 3, pad, ny,
-                                                                  nx, TY, TX, zx, fuse);
-      else
-        rf_x_kernel<false, true, 5><<<xb, kRfXWarps * 32, 0, st>>>(g, nullptr, cxp, n_units, 0, NY, NX, 0, 0, 0, 3,
-                                                                   pad, ny, nx, TY, TX, zx, fuse);
-    } else if (it == 0) {
+    if (it == 0) {
       rf_x_kernel<true, true><<<xb, kRfXWarps * 32, 0, st>>>(g, in, cxp, n_units, 0, NY, NX, 0, 0, 0, 3, pad, ny, nx,
                                                              TY, TX, zx, fuse);
     } else {

@@ -348,3 +348,30 @@ def test_cuda_filter_launch_groups_are_equivalent(monkeypatch):
         np.testing.assert_array_equal(a, b)
     want = rfo.recursive_filter(np.ma.masked_array(data, mask), cx, cy, 2, 3)
     np.testing.assert_array_equal(split[1], np.ma.getdata(want))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 150, 40), (5, 97, 131), (37, 40, 70)])
+def test_cuda_fused_and_separate_sweeps_agree(monkeypatch, shape):
+    """The tile-row wavefront (y-forward inside the x-backward sweep, the default) and the separate
+    sweeps (NBH_RF_FUSE=0) are the same arithmetic: bit-identical results, also against the oracle,
+    with one slice (all tile rows of a slice in one block) and with more slices than a block holds."""
+    import torch
+
+    from improver_b200 import engine
+
+    rng = np.random.default_rng(33)
+    ny, nx = shape[-2:]
+    data = rng.random(shape).astype(np.float32)
+    data[data < 0.25] = 0.0
+    cx = (rng.random((ny, nx - 1)) * 0.5).astype(np.float32)
+    cy = (rng.random((ny - 1, nx)) * 0.5).astype(np.float32)
+    args = (torch.from_numpy(data).cuda(), torch.from_numpy(cx).cuda(), torch.from_numpy(cy).cuda())
+    for mask_zeros in (False, True):
+        fused = engine.recursive_filter(*args, 2, 15, mask_zeros=mask_zeros).cpu().numpy()
+        monkeypatch.setenv("NBH_RF_FUSE", "0")
+        separate = engine.recursive_filter(*args, 2, 15, mask_zeros=mask_zeros).cpu().numpy()
+        monkeypatch.delenv("NBH_RF_FUSE")
+        np.testing.assert_array_equal(fused, separate)
+        want = rfo.recursive_filter(data, cx, cy, 2, 15, mask_zeros=mask_zeros)
+        np.testing.assert_array_equal(fused, np.ma.getdata(want))
