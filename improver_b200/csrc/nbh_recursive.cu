@@ -19,6 +19,8 @@
 //                reflection (no separate halo pass)
 //   rf_y_kernel  one thread per (slice, column): walks down, then up, a batch of rows per
 //                step; the last iteration's upward walk writes the un-padded output directly
+//   fusion       by default the downward (y-forward) walk runs inside rf_x_kernel's backward
+//                sweep as a tile-row wavefront (see RfFuse) and rf_y_kernel only walks up
 // A chain step itself is FMUL + FADD = 8 cycles; both kernels are bound by memory traffic.
 #include "nbh_common.cuh"
 
