@@ -44,12 +44,18 @@ square_tile_kernel(const __grid_constant__ SqParams p, const SqTileGeom g) {
   const bool wrap = (p.flags & NBH_WRAP_X) != 0;
   const bool sum_only = (p.flags & NBH_SUM_ONLY) != 0;
 
-  long long b = blockIdx.x;
-  const int tx = (int)(b % g.tiles_x); b /= g.tiles_x;
-  const int ty = (int)(b % g.tiles_y); b /= g.tiles_y;
-  const long long unit = b;
-  const long long plane = unit / p.n_thr;
-  const int t = (int)(unit - plane * p.n_thr);
+  // 32-bit index arithmetic: the grid has fewer than 2^31 blocks, and 64-bit divisions in every
+  // thread's prologue were a quarter of the kernel's instructions
+  unsigned b = blockIdx.x;
+  const unsigned tiles_x = (unsigned)g.tiles_x, tiles_y = (unsigned)g.tiles_y, n_thr = (unsigned)p.n_thr;
+  const unsigned bq = b / tiles_x;
+  const int tx = (int)(b - bq * tiles_x);
+  const unsigned unit_u = bq / tiles_y;
+  const int ty = (int)(bq - unit_u * tiles_y);
+  const unsigned plane_u = n_thr > 1 ? unit_u / n_thr : unit_u;
+  const long long unit = unit_u;
+  const long long plane = plane_u;
+  const int t = (int)(unit_u - plane_u * n_thr);
   const ThrDev& thr = p.thr.t[TM ? t : 0];
   const int x0 = tx * kTileTX, y0 = ty * kTileTY;
   const float* src = p.in + plane * p.plane_stride;
