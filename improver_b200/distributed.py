@@ -79,12 +79,16 @@ def neighbourhood_y_tiled(band: torch.Tensor, cells: int, mask_band: Optional[to
     """Neighbourhood of a y-tiled grid: halo exchange, kernels on the extended
     band, crop.  `band` is this rank's (..., rows, nx) CUDA tensor.  Equal to
     the untiled result except for the reference's ones-trimming edge behaviour,
-    whose bounding boxes are global (not reproduced in tiled mode)."""
+    whose bounding boxes are global (not reproduced in tiled mode).  The launch uses the
+    kernels with exact window sums (`engine.exact_square_sums`): their result does not depend
+    on the row a band starts at, so the bands reproduce the untiled exact-sum result bit for
+    bit (the float32 running sums of the default tile kernel agree with it to ~1e-7)."""
     from . import engine
 
     ext = exchange_halo_rows(band, cells, group)
     m_ext = exchange_halo_rows(mask_band, cells, group) if mask_band is not None else None
-    out, omask, status = engine.neighbourhood(ext, cells, mask2d=m_ext, **kwargs)
+    with engine.exact_square_sums():
+        out, omask, status = engine.neighbourhood(ext, cells, mask2d=m_ext, **kwargs)
     out = crop_own_rows(out, cells, group)
     if omask is not None:
         omask = crop_own_rows(omask, cells, group)

@@ -7,6 +7,7 @@ all arithmetic happens in libimprover_b200.so through the C ABI
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 import ctypes as C
@@ -59,6 +60,23 @@ def check_status(status: torch.Tensor) -> int:
     if nan_flag:
         raise ValueError(NAN_MESSAGE)
     return fixed
+
+
+@contextlib.contextmanager
+def exact_square_sums():
+    """Within this context single-member square launches use the kernels with exact window sums
+    (float64 / fixed point: `square_rs_kernel` rows mode and the warp / block kernels) instead of
+    the float32 running sums of `square_tile_kernel`.  Their results do not depend on where a tile
+    starts, so a y-band of a grid reproduces the rows of the whole grid bit for bit."""
+    old = os.environ.get("NBH_SQ_TILE")
+    os.environ["NBH_SQ_TILE"] = "0"
+    try:
+        yield
+    finally:
+        if old is None:
+            del os.environ["NBH_SQ_TILE"]
+        else:
+            os.environ["NBH_SQ_TILE"] = old
 
 
 def neighbourhood(
