@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libimprover_b200.so")
-SOURCES = ["nbh_capi.cu", "nbh_square.cu", "nbh_square_v1.cu", "nbh_square_v2.cu", "nbh_square_v4.cu", "nbh_square_w1.cu", "nbh_square_w2.cu", "nbh_square_w4.cu", "nbh_square_tma.cu", "nbh_square_rs.cu", "nbh_square_tile.cu", "nbh_square_mt.cu", "nbh_circular.cu", "nbh_percentile.cu", "nbh_threshold.cu", "nbh_vicinity.cu", "nbh_recursive.cu"]
+SOURCES = ["nbh_capi.cu", "nbh_square.cu", "nbh_square_v1.cu", "nbh_square_v2.cu", "nbh_square_v4.cu", "nbh_square_w1.cu", "nbh_square_w2.cu", "nbh_square_w4.cu", "nbh_square_tma.cu", "nbh_square_rs.cu", "nbh_square_tile.cu", "nbh_square_mt.cu", "nbh_circular.cu", "nbh_percentile.cu", "nbh_threshold.cu", "nbh_vicinity.cu", "nbh_recursive.cu", "nbh_tiling.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",

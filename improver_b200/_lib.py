@@ -14,7 +14,7 @@ LIBPATH = os.environ.get("IMPROVER_B200_LIB", os.path.join(_HERE, "lib", "libimp
 OPS = {">": 0, "gt": 0, "GT": 0, ">=": 1, "ge": 1, "GE": 1,
        "<": 2, "lt": 2, "LT": 2, "<=": 3, "le": 3, "LE": 3, "==": 4, "eq": 4, "EQ": 4}
 
-SUM_ONLY, WRAP_X, WEIGHTED = 1, 2, 4
+SUM_ONLY, WRAP_X, WEIGHTED, EXACT_SUMS, LAND_SEA = 1, 2, 4, 8, 16
 
 
 class NbhThreshold(C.Structure):
@@ -30,7 +30,15 @@ class NbhDesc(C.Structure):
         ("n_thresholds", C.c_int32), ("flags", C.c_int32),
         ("thresholds", C.POINTER(NbhThreshold)),
         ("mask2d", C.c_void_p), ("mask_nd", C.c_void_p),
+        ("plane_cells", C.POINTER(C.c_int32)),
+        ("y_offset", C.c_int32), ("ny_global", C.c_int32), ("halo_top", C.c_int32), ("halo_bottom", C.c_int32),
+        ("ext_stats", C.c_void_p),
     ]
+
+
+class NbhSliceStats(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("y0min", "y0max", "x0min", "x0max", "y1min", "y1max", "x1min", "x1max",
+                                         "vmin_key", "vmax_key")]
 
 
 class EngineError(RuntimeError):
@@ -59,6 +67,19 @@ def load() -> C.CDLL:
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(NbhDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                        C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.nbh_slice_stats_f32.restype = C.c_int
+    lib.nbh_slice_stats_f32.argtypes = [C.POINTER(NbhDesc), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.nbh_halo_pack.restype = C.c_int
+    lib.nbh_halo_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.nbh_halo_unpack.restype = C.c_int
+    lib.nbh_halo_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p]
+    lib.nbh_halo_exchange_workspace_bytes.restype = C.c_size_t
+    lib.nbh_halo_exchange_workspace_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32]
+    lib.nbh_halo_exchange.restype = C.c_int
+    lib.nbh_halo_exchange.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.nbh_percentiles_f32.restype = C.c_int
     lib.nbh_percentiles_f32.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int32,
                                         C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
@@ -90,7 +111,7 @@ def load() -> C.CDLL:
     lib.nbh_profile_last_ms.argtypes = [C.POINTER(C.c_float)]
     lib.nbh_profile_last_kernel.restype = C.c_char_p
     lib.nbh_profile_last_kernel.argtypes = []
-    if lib.nbh_version() != 1:
+    if lib.nbh_version() != 2:
         raise ImportError("libimprover_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -102,7 +123,8 @@ def check(rc: int) -> None:
         raise EngineError(msg or f"native call failed with code {rc}")
 
 
-EXPORTED = ["nbh_version", "nbh_last_error", "nbh_device_info", "nbh_workspace_bytes",
+EXPORTED = ["nbh_version", "nbh_last_error", "nbh_device_info", "nbh_workspace_bytes", "nbh_slice_stats_f32",
+            "nbh_halo_pack", "nbh_halo_unpack", "nbh_halo_exchange", "nbh_halo_exchange_workspace_bytes",
             "nbh_square_f32", "nbh_circular_f32", "nbh_percentiles_f32",
             "nbh_percentiles_workspace_bytes", "nbh_threshold_f32", "nbh_threshold_vicinity_f32", "nbh_vicinity_f32",
             "nbh_recursive_filter_f32", "nbh_recursive_filter_workspace_bytes", "nbh_recurse_f32",

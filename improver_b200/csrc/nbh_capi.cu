@@ -166,6 +166,117 @@ int run_threshold_vicinity(const float* in, const uint8_t* mask_nd, const uint8_
                            long long n_planes, int ny, int nx, int32_t* status, cudaStream_t st, int raw_op = -1);
 int run_threshold(const float*, const uint8_t*, float*, int32_t*, const NbhThreshold*, int, long long,
                   long long, int32_t*, cudaStream_t);
+int run_slice_stats(const NbhDesc*, const float*, NbhSliceStats*, cudaStream_t);
+int run_halo_pack(const float*, float*, float*, float*, long long, int, int, int, int, int, cudaStream_t);
+int run_halo_unpack(float*, const float*, const float*, long long, int, int, int, int, cudaStream_t);
+size_t halo_exchange_workspace_bytes(long long, int, int);
+int run_halo_exchange(void*, int, int, const float*, float*, long long, int, int, int, void*, size_t, cudaStream_t);
+
+typedef int (*nbhood_fn)(const NbhDesc*, const float*, float*, uint8_t*, int32_t*, void*, size_t, cudaStream_t);
+
+// OR the status words of a sub-launch into the caller's (status[0] is a flag, status[1] a count)
+__global__ void merge_status_kernel(int32_t* dst, const int32_t* src) {
+  if (threadIdx.x == 0) { dst[0] |= src[0]; dst[1] += src[1]; }
+}
+
+bool square_native_land_sea(const NbhDesc&);
+bool circular_native_land_sea(const NbhDesc&);
+
+__global__ void invert_mask_kernel(const uint8_t* m, uint8_t* inv, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) inv[i] = m[i] == 0 ? 1 : 0;
+}
+// out = land point ? land result : sea result (filled(0) sum of the two re-masked passes,
+// cli/nbhood_land_and_sea.py:176-184); nothing is masked in the combined field
+__global__ void land_sea_combine_kernel(float* out, const float* sea, uint8_t* out_mask, const uint8_t* land,
+                                        long long n_out, long long per_slice) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (land[i % per_slice] == 0) out[i] = sea[i];
+    if (out_mask) out_mask[i] = 0;
+  }
+}
+
+static size_t land_sea_extra_bytes(const NbhDesc& d) {
+  const size_t per = (size_t)d.ny * d.nx;
+  const size_t T = d.n_thresholds > 0 ? d.n_thresholds : 1;
+  return (per + 255) / 256 * 256 + ((size_t)d.n_planes * T * per * 4 + 255) / 256 * 256 + 256;
+}
+
+// Generic land + sea launch for the kernels without a native NBH_LAND_SEA path: two masked
+// launches (land mask, inverted mask) and a select.
+static int run_land_sea_composite(nbhood_fn fn, const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
+                                  int32_t* status, void* ws, size_t ws_bytes, cudaStream_t st) {
+  NBH_REQUIRE(d->mask2d != nullptr, "NBH_LAND_SEA needs the land mask as mask2d");
+  NBH_REQUIRE(d->ny > 0 && d->nx > 0 && d->n_planes > 0, "empty grid");
+  const size_t extra = land_sea_extra_bytes(*d);
+  NBH_REQUIRE(ws_bytes >= extra, "workspace too small");
+  const size_t per = (size_t)d->ny * d->nx;
+  const size_t T = d->n_thresholds > 0 ? d->n_thresholds : 1;
+  unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+  uint8_t* inv = base;
+  float* sea = reinterpret_cast<float*>(base + (per + 255) / 256 * 256);
+  int32_t* sub_status = reinterpret_cast<int32_t*>(base + extra - 256);
+  void* sub_ws = base + extra;
+  const size_t sub_bytes = ws_bytes - extra;
+  invert_mask_kernel<<<(unsigned)((per + 255) / 256), 256, 0, st>>>(d->mask2d, inv, (long long)per);
+  NbhDesc sub = *d;
+  sub.flags &= ~NBH_LAND_SEA;
+  int rc = fn(&sub, in, out, nullptr, status, sub_ws, sub_bytes, st);
+  if (rc) return rc;
+  sub.mask2d = inv;
+  rc = fn(&sub, in, sea, nullptr, sub_status, sub_ws, sub_bytes, st);
+  if (rc) return rc;
+  merge_status_kernel<<<1, 32, 0, st>>>(status, sub_status);
+  const long long n_out = (long long)d->n_planes * T * per;
+  land_sea_combine_kernel<<<(unsigned)min((n_out + 255) / 256, (long long)sm_count() * 16), 256, 0, st>>>(
+      out, sea, out_mask, d->mask2d, n_out, (long long)per);
+  NBH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int dispatch_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask, int32_t* status,
+                           void* ws, size_t ws_bytes, cudaStream_t st) {
+  if ((d->flags & NBH_LAND_SEA) && !square_native_land_sea(*d))
+    return run_land_sea_composite(run_square, d, in, out, out_mask, status, ws, ws_bytes, st);
+  return run_square(d, in, out, out_mask, status, ws, ws_bytes, st);
+}
+static int dispatch_circular(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask, int32_t* status,
+                             void* ws, size_t ws_bytes, cudaStream_t st) {
+  if ((d->flags & NBH_LAND_SEA) && !circular_native_land_sea(*d))
+    return run_land_sea_composite(run_circular, d, in, out, out_mask, status, ws, ws_bytes, st);
+  return run_circular(d, in, out, out_mask, status, ws, ws_bytes, st);
+}
+
+// Lead-time dependent radii (nbhood.py:438-455: one radius per slice): consecutive planes with
+// the same radius form one launch.  The sub-launches share the workspace (stream order) and
+// report through a private status pair at its end.
+static int run_per_plane_radii(nbhood_fn fn, const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
+                               int32_t* status, void* ws, size_t ws_bytes, cudaStream_t st) {
+  NBH_REQUIRE(d->n_planes > 0 && d->ny > 0 && d->nx > 0, "empty grid");
+  NBH_REQUIRE(ws_bytes >= 256, "workspace too small");
+  NBH_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int32_t), st));
+  int32_t* sub_status = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(ws) + (ws_bytes - 256) / 256 * 256);
+  const size_t sub_ws = (ws_bytes - 256) / 256 * 256;
+  const long long out_plane = (long long)(d->n_thresholds > 0 ? d->n_thresholds : 1) * d->ny * d->nx;
+  for (long long p0 = 0; p0 < d->n_planes;) {
+    long long p1 = p0 + 1;
+    while (p1 < d->n_planes && d->plane_cells[p1] == d->plane_cells[p0]) ++p1;
+    NbhDesc sub = *d;
+    sub.plane_cells = nullptr;
+    sub.cells = d->plane_cells[p0];
+    sub.n_planes = p1 - p0;
+    if (sub.ext_stats) sub.ext_stats += p0 * d->n_members * (d->n_thresholds > 0 ? d->n_thresholds : 1);
+    if (sub.mask_nd) sub.mask_nd += p0 * d->plane_stride;
+    const int rc = fn(&sub, in + p0 * d->plane_stride, out + p0 * out_plane,
+                      out_mask ? out_mask + p0 * out_plane : nullptr, sub_status, ws, sub_ws, st);
+    if (rc) return rc;
+    merge_status_kernel<<<1, 32, 0, st>>>(status, sub_status);
+    p0 = p1;
+  }
+  NBH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 }  // namespace nbh
 
@@ -203,21 +314,71 @@ int nbh_device_info(int32_t* sm_count, int64_t* smem_optin_bytes) {
 
 size_t nbh_workspace_bytes(const NbhDesc* desc) {
   if (!desc) return 0;
+  if (desc->plane_cells) {
+    // the largest request of any radius group, plus the private status words of the sub-launches
+    size_t best = 0;
+    for (long long p = 0; p < desc->n_planes; ++p) {
+      if (p > 0 && desc->plane_cells[p] == desc->plane_cells[p - 1]) continue;
+      NbhDesc sub = *desc;
+      sub.plane_cells = nullptr;
+      sub.cells = desc->plane_cells[p];
+      const size_t b = nbh_workspace_bytes(&sub);
+      best = b > best ? b : best;
+    }
+    return (best + 255) / 256 * 256 + 512;
+  }
   size_t a = nbh::square_workspace_bytes(*desc);
   size_t b = nbh::circular_workspace_bytes(*desc);
-  return a > b ? a : b;
+  size_t need = a > b ? a : b;
+  if (desc->flags & NBH_LAND_SEA) need += nbh::land_sea_extra_bytes(*desc);
+  return need;
 }
 
 int nbh_square_f32(const NbhDesc* desc, const float* in, float* out, uint8_t* out_mask, int32_t* status,
                    void* workspace, size_t workspace_bytes, void* stream) {
-  return nbh::run_square(desc, in, out, out_mask, status, workspace, workspace_bytes,
-                         static_cast<cudaStream_t>(stream));
+  NBH_REQUIRE(desc != nullptr, "null descriptor");
+  if (desc->plane_cells)
+    return nbh::run_per_plane_radii(nbh::dispatch_square, desc, in, out, out_mask, status, workspace, workspace_bytes,
+                                    static_cast<cudaStream_t>(stream));
+  return nbh::dispatch_square(desc, in, out, out_mask, status, workspace, workspace_bytes,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int nbh_circular_f32(const NbhDesc* desc, const float* in, float* out, uint8_t* out_mask, int32_t* status,
                      void* workspace, size_t workspace_bytes, void* stream) {
-  return nbh::run_circular(desc, in, out, out_mask, status, workspace, workspace_bytes,
-                           static_cast<cudaStream_t>(stream));
+  NBH_REQUIRE(desc != nullptr, "null descriptor");
+  if (desc->plane_cells)
+    return nbh::run_per_plane_radii(nbh::dispatch_circular, desc, in, out, out_mask, status, workspace, workspace_bytes,
+                                    static_cast<cudaStream_t>(stream));
+  return nbh::dispatch_circular(desc, in, out, out_mask, status, workspace, workspace_bytes,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int nbh_slice_stats_f32(const NbhDesc* desc, const float* in, NbhSliceStats* stats, void* stream) {
+  return nbh::run_slice_stats(desc, in, stats, static_cast<cudaStream_t>(stream));
+}
+
+int nbh_halo_pack(const float* band, float* ext, float* send_up, float* send_down, int64_t n_slices, int32_t rows,
+                  int32_t nx, int32_t cells, int32_t halo_top, int32_t halo_bottom, void* stream) {
+  return nbh::run_halo_pack(band, ext, send_up, send_down, n_slices, rows, nx, cells, halo_top, halo_bottom,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int nbh_halo_unpack(float* ext, const float* recv_up, const float* recv_down, int64_t n_slices, int32_t rows,
+                    int32_t nx, int32_t halo_top, int32_t halo_bottom, void* stream) {
+  return nbh::run_halo_unpack(ext, recv_up, recv_down, n_slices, rows, nx, halo_top, halo_bottom,
+                              static_cast<cudaStream_t>(stream));
+}
+
+size_t nbh_halo_exchange_workspace_bytes(int64_t n_slices, int32_t nx, int32_t cells) {
+  return nbh::halo_exchange_workspace_bytes(n_slices, nx, cells);
+}
+
+int nbh_halo_exchange(void* nccl_comm, int32_t rank, int32_t n_ranks, const float* band, float* ext,
+                      int64_t n_slices, int32_t rows, int32_t nx, int32_t cells, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return nbh::run_halo_exchange(nccl_comm, rank, n_ranks, band, ext, n_slices, rows, nx, cells, workspace,
+                                workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int nbh_percentiles_f32(const float* in, float* out, const float* pct, int32_t n_pct, int64_t n_slices,

@@ -15,8 +15,6 @@
 
 namespace nbh {
 
-int env_int(const char* name, int dflt);
-
 struct CircParams {
   const float* in;
   float* out;
@@ -206,34 +204,82 @@ __global__ void circ_tables_kernel(double* ktab, int* wtab, float* area_const, i
 
 
 // ---------------------------------------------------------------------------
-// Large radii: the 2r+1-row prefix ring no longer fits in shared memory (and a
-// strip cannot even hold the 2r halo), so the float64 row prefixes of a batch
-// of planes are written to global memory once (they stay L2-resident: a UK
-// plane is 8 MB) and every output gathers 2 prefix values per kernel row.
+// Unweighted discs of any radius: row-span decomposition over row prefix sums.
+//
+// Pass 1 (circ_prefix_kernel) writes the inclusive row prefix of the (thresholded, masked,
+// member-summed) field of a batch of planes to the workspace; pass 2 (the gather kernels) forms
+// every output as the sum over the 2r+1 kernel rows of a prefix difference, with the
+// edge-replication terms of scipy's mode="nearest".
+//
+// Prefix type PT.  Values known to lie in [0, 1] (truth values; raw probabilities are tried
+// speculatively, see `guard`) are turned into fixed point (P * 2^fx_shift, round to nearest) and
+// the row prefix is an unsigned 32-bit sum whose wrap-around cancels in every span difference
+// ((2r+1) * R * 2^fx_shift < 2^32); the spans are accumulated in 64 bits.  Half the bytes per
+// prefix value and integer adds instead of DADDs; the quantisation contributes at most
+// 2^-(fx_shift+1) to a mean.  Anything else uses float64 prefixes like the reference's float64
+// correlate.
+//
+// NBH_LAND_SEA: two prefix planes, land * v and sea * v; a point gathers from the plane of its
+// own surface type only, and is normalised by the area of that type (A_sea = sum(K) - A_land,
+// exact: mode="nearest" maps every kernel cell to some grid cell).
 // ---------------------------------------------------------------------------
+constexpr int kCircParamRadius = 400;          // widths table passed as a kernel parameter up to this radius
+
+struct CircWidths { short w[2 * kCircParamRadius + 2]; };     // w[dy + r], dy = -r..r
+
 struct CircGlobalParams {
   const float* in;
   float* out;
   uint8_t* out_mask;
   const uint8_t* mask2d;
   const uint8_t* mask_nd;
-  const float* area;
-  const int* wtab;
-  double* prefix;        // [batch][ny][nx] inclusive row prefix of the member-summed, masked values
-  double* cprefix;       // MASKND: same for the valid mask
+  const float* area;     // mask2d launches: area of the own surface type (LAND_SEA) / of the valid cells
+  const int* wtab;       // half width per |dy| (radii beyond kCircParamRadius)
+  void* prefix;          // [batch][ny][nx] inclusive row prefix (PT) of the member-summed, masked values
+  void* prefix2;         // LAND_SEA: same for the complementary (sea) points
+  double* cprefix;       // MASKND: same for the valid mask (float64 path only)
   int32_t* status;
+  int* guard;            // [0]: set by the speculative fixed-point prefix pass when a raw value lies
+                         // outside [0, 1]; the float64 kernels of a speculative launch exit while it is 0
   long long plane_stride, member_stride;
   long long plane0;      // first plane of this batch
   int n_batch;
   int n_members, ny, nx, r;
   int flags, n_thr, t;
+  int guarded;           // 1: this is the float64 re-run of a speculative launch (exit unless *guard)
+  int check_range;       // 1: fixed-point pass over raw data: flag values outside [0, 1]
   double inv_members;
   float area_const;
+  float fx_scale;        // 2^fx_shift
+  double fx_inv;         // 2^-fx_shift
   ThrDev thr;
 };
 
+template <typename PT> struct CircAcc;
+template <> struct CircAcc<double> {
+  typedef double acc_t;
+  static __device__ __forceinline__ double cvt(float P, float) { return (double)P; }
+  static __device__ __forceinline__ double result(double S, double) { return S; }
+};
+template <> struct CircAcc<unsigned> {
+  typedef unsigned long long acc_t;
+  static __device__ __forceinline__ unsigned cvt(float P, float scale) { return __float2uint_rn(P * scale); }
+  static __device__ __forceinline__ double result(unsigned long long S, double inv) { return (double)S * inv; }
+};
+
+template <typename PT> __device__ __forceinline__ PT warp_incl_scan(PT v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const PT o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
 // one warp per (plane, row): member sum + inclusive prefix along x
+template <typename PT, bool LS>
 __global__ void __launch_bounds__(256) circ_prefix_kernel(const CircGlobalParams p) {
+  if (p.guarded && *p.guard == 0) return;
   const int lane = threadIdx.x & 31;
   const long long row_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row_id >= (long long)p.n_batch * p.ny) return;
@@ -242,127 +288,149 @@ __global__ void __launch_bounds__(256) circ_prefix_kernel(const CircGlobalParams
   const float* in_row = p.in + plane * p.plane_stride + (long long)y * p.nx;
   const uint8_t* mnd_row = p.mask_nd ? p.mask_nd + plane * p.plane_stride + (long long)y * p.nx : nullptr;
   const uint8_t* m2_row = p.mask2d ? p.mask2d + (long long)y * p.nx : nullptr;
-  double* pre = p.prefix + ((long long)b * p.ny + y) * p.nx;
+  PT* pre = reinterpret_cast<PT*>(p.prefix) + ((long long)b * p.ny + y) * p.nx;
+  PT* pre2 = LS ? reinterpret_cast<PT*>(p.prefix2) + ((long long)b * p.ny + y) * p.nx : nullptr;
   double* cpre = p.cprefix ? p.cprefix + ((long long)b * p.ny + y) * p.nx : nullptr;
-  double carry = 0.0, ccarry = 0.0;
+  PT carry = 0, carry2 = 0;
+  double ccarry = 0.0;
   float nanacc = 0.f;
+  bool bad = false;
   for (int x0 = 0; x0 < p.nx; x0 += 32) {
     const int x = x0 + lane;
     float P = 0.f, okf = 0.f;
+    bool land = true;
     if (x < p.nx) {
       const bool m2 = m2_row ? (m2_row[x] != 0) : true;
-      bool valid = m2, seen = true;
+      land = m2;
+      bool valid = LS ? true : m2, seen = true;
       if (mnd_row) { seen = mnd_row[x] == 0; valid = valid && seen; }
       for (int m = 0; m < p.n_members; ++m) {
         const float d = __ldg(in_row + (long long)m * p.member_stride + x);
         if (seen) nanacc = max_nan(nanacc, fabsf(d));
+        if (p.check_range && !(d >= 0.f && d <= 1.f)) bad = true;
         const float tv = p.thr.mode ? truth_value(d, p.thr) : d;
         P += valid ? tv : 0.f;
       }
       okf = valid ? 1.f : 0.f;
     }
-    double incl = (double)P, cincl = (double)okf;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const double o = __shfl_up_sync(0xffffffffu, incl, d);
-      const double oc = __shfl_up_sync(0xffffffffu, cincl, d);
-      if (lane >= d) { incl += o; cincl += oc; }
-    }
-    if (x < p.nx) {
-      pre[x] = carry + incl;
-      if (cpre) cpre[x] = ccarry + cincl;
-    }
+    const PT q = CircAcc<PT>::cvt(P, p.fx_scale);
+    const PT incl = warp_incl_scan<PT>(LS ? (land ? q : (PT)0) : q, lane);
+    if (x < p.nx) pre[x] = carry + incl;
     carry += __shfl_sync(0xffffffffu, incl, 31);
-    ccarry += __shfl_sync(0xffffffffu, cincl, 31);
+    if (LS) {
+      const PT incl2 = warp_incl_scan<PT>(land ? (PT)0 : q, lane);
+      if (x < p.nx) pre2[x] = carry2 + incl2;
+      carry2 += __shfl_sync(0xffffffffu, incl2, 31);
+    }
+    if (cpre) {
+      const double cincl = warp_incl_scan<double>((double)okf, lane);
+      if (x < p.nx) cpre[x] = ccarry + cincl;
+      ccarry += __shfl_sync(0xffffffffu, cincl, 31);
+    }
   }
   if (__any_sync(0xffffffffu, __isnanf(nanacc)) && lane == 0)
     atomicOr(reinterpret_cast<unsigned*>(p.status), 1u);
+  if (p.check_range && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(p.guard, 1);
 }
 
 // extended inclusive prefix of a periodic row: E(c) for any c in [-nx, 2nx)
-__device__ __forceinline__ double wrap_prefix(const double* pre, int c, int nx) {
-  const double total = pre[nx - 1];
+template <typename PT> __device__ __forceinline__ PT wrap_prefix(const PT* pre, int c, int nx) {
+  const PT total = pre[nx - 1];
   if (c < 0) return pre[c + nx] - total;
   if (c >= nx) return pre[c - nx] + total;
   return pre[c];
 }
 
-__device__ __forceinline__ double span_sum_wrap(const double* pre, int x, int w, int nx) {
-  return wrap_prefix(pre, x + w, nx) - wrap_prefix(pre, x - w - 1, nx);
+template <typename PT> __device__ __forceinline__ PT span_sum_wrap(const PT* pre, int x, int w, int nx) {
+  return wrap_prefix<PT>(pre, x + w, nx) - wrap_prefix<PT>(pre, x - w - 1, nx);
 }
 
-__device__ __forceinline__ double span_sum(const double* pre, int x, int w, int nx) {
+template <typename PT> __device__ __forceinline__ PT span_sum(const PT* pre, int x, int w, int nx) {
   const int lo = max(x - w, 0), hi = min(x + w, nx - 1);
-  double s = pre[hi] - (lo > 0 ? pre[lo - 1] : 0.0);
+  PT s = pre[hi] - (lo > 0 ? pre[lo - 1] : (PT)0);
   const int nl = lo - (x - w), nr = (x + w) - hi;     // replicated edge cells (mode="nearest")
-  if (nl > 0) s += (double)nl * pre[0];
-  if (nr > 0) s += (double)nr * (pre[nx - 1] - (nx > 1 ? pre[nx - 2] : 0.0));
+  if (nl > 0) s += (PT)nl * pre[0];
+  if (nr > 0) s += (PT)nr * (pre[nx - 1] - (nx > 1 ? pre[nx - 2] : (PT)0));
   return s;
 }
 
-__global__ void __launch_bounds__(256) circ_gather_kernel(const CircGlobalParams p) {
-  extern __shared__ int wtab_s[];
-  for (int k = threadIdx.x; k <= p.r; k += blockDim.x) wtab_s[k] = p.wtab[k];
-  __syncthreads();
+template <typename PT>
+__device__ __forceinline__ void circ_store(const CircGlobalParams& p, typename CircAcc<PT>::acc_t S, double A,
+                                           bool have_A, long long plane, long long pt, long long per_plane) {
+  const long long o = (plane * p.n_thr + p.t) * per_plane + pt;
+  const double Sd = CircAcc<PT>::result(S, p.fx_inv);
+  float res;
+  if (p.flags & NBH_SUM_ONLY) {
+    res = (float)Sd;
+  } else {
+    const float Af = have_A ? (float)A : (p.mask2d ? p.area[pt] : p.area_const);
+    res = (Af == 0.f) ? __int_as_float(0x7fc00000) : (float)(Sd / (double)Af * p.inv_members);
+  }
+  p.out[o] = res;
+  if (p.out_mask) {
+    bool masked = (p.mask2d && !(p.flags & NBH_LAND_SEA)) ? (p.mask2d[pt] == 0) : false;
+    if (p.mask_nd) masked = masked || (p.mask_nd[plane * p.plane_stride + pt] != 0);
+    p.out_mask[o] = masked ? 1 : 0;
+  }
+}
+
+// direct gather (prefix values from L1 / L2): any radius
+template <typename PT, bool LS, bool PW>
+__global__ void __launch_bounds__(256)
+circ_gather_kernel(const CircGlobalParams p, const __grid_constant__ CircWidths cw) {
+  if (p.guarded && *p.guard == 0) return;
+  typedef typename CircAcc<PT>::acc_t acc_t;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long per_plane = (long long)p.ny * p.nx;
   if (i >= (long long)p.n_batch * per_plane) return;
   const int b = (int)(i / per_plane);
   const long long pt = i - (long long)b * per_plane;
   const int y = (int)(pt / p.nx), x = (int)(pt % p.nx);
-  const double* pre = p.prefix + (long long)b * per_plane;
+  const bool sea = LS && p.mask2d[pt] == 0;
+  const PT* pre = reinterpret_cast<const PT*>(sea ? p.prefix2 : p.prefix) + (long long)b * per_plane;
   const double* cpre = p.cprefix ? p.cprefix + (long long)b * per_plane : nullptr;
-  double S = 0.0, A = 0.0;
-  if (!(p.flags & NBH_WRAP_X) && !cpre && x - p.r - 1 >= 0 && x + p.r <= p.nx - 1) {
+  acc_t S = 0;
+  double A = 0.0;
+  const int r = p.r;
+  if (!(p.flags & NBH_WRAP_X) && !cpre && x - r - 1 >= 0 && x + r <= p.nx - 1) {
     // every span lies inside the row: two loads and two adds per kernel row
-    for (int dy = -p.r; dy <= p.r; ++dy) {
-      const int w = wtab_s[dy < 0 ? -dy : dy];
-      const double* row = pre + (long long)min(max(y + dy, 0), p.ny - 1) * p.nx + x;
-      S += row[w] - row[-w - 1];
+#pragma unroll 4
+    for (int dy = -r; dy <= r; ++dy) {
+      const int w = PW ? (int)cw.w[dy + r] : p.wtab[dy < 0 ? -dy : dy];
+      const PT* row = pre + (long long)min(max(y + dy, 0), p.ny - 1) * p.nx + x;
+      S += (acc_t)(PT)(row[w] - row[-w - 1]);
     }
-  } else
-  for (int dy = -p.r; dy <= p.r; ++dy) {
-    const int w = wtab_s[dy < 0 ? -dy : dy];
-    const int ys = min(max(y + dy, 0), p.ny - 1);
-    if (p.flags & NBH_WRAP_X) {
-      S += span_sum_wrap(pre + (long long)ys * p.nx, x, w, p.nx);
-      if (cpre) A += span_sum_wrap(cpre + (long long)ys * p.nx, x, w, p.nx);
-    } else {
-      S += span_sum(pre + (long long)ys * p.nx, x, w, p.nx);
-      if (cpre) A += span_sum(cpre + (long long)ys * p.nx, x, w, p.nx);
-    }
-  }
-  const long long plane = p.plane0 + b;
-  const long long o = (plane * p.n_thr + p.t) * per_plane + pt;
-  float res;
-  if (p.flags & NBH_SUM_ONLY) {
-    res = (float)S;
   } else {
-    const float Af = cpre ? (float)A : (p.mask2d ? p.area[pt] : p.area_const);
-    res = (Af == 0.f) ? __int_as_float(0x7fc00000) : (float)(S / (double)Af * p.inv_members);
+    for (int dy = -r; dy <= r; ++dy) {
+      const int w = PW ? (int)cw.w[dy + r] : p.wtab[dy < 0 ? -dy : dy];
+      const int ys = min(max(y + dy, 0), p.ny - 1);
+      if (p.flags & NBH_WRAP_X) {
+        S += (acc_t)span_sum_wrap<PT>(pre + (long long)ys * p.nx, x, w, p.nx);
+        if (cpre) A += span_sum_wrap<double>(cpre + (long long)ys * p.nx, x, w, p.nx);
+      } else {
+        S += (acc_t)span_sum<PT>(pre + (long long)ys * p.nx, x, w, p.nx);
+        if (cpre) A += span_sum<double>(cpre + (long long)ys * p.nx, x, w, p.nx);
+      }
+    }
   }
-  p.out[o] = res;
-  if (p.out_mask) {
-    bool masked = p.mask2d ? (p.mask2d[pt] == 0) : false;
-    if (p.mask_nd) masked = masked || (p.mask_nd[plane * p.plane_stride + pt] != 0);
-    p.out_mask[o] = masked ? 1 : 0;
-  }
+  circ_store<PT>(p, S, A, cpre != nullptr, p.plane0 + b, pt, per_plane);
 }
 
-
-// Shared-memory tiled gather: a block stages the (TH + 2r) x (TW + 2r + 1)
-// window of prefix values its TH x TW outputs need (each value is then read
-// ~2(2r+1) times from shared memory instead of L2).
+// Shared-memory tiled gather: a block stages the (TH + 2r) x (TW + 2r + 1) window of prefix
+// values its TH x TW outputs need (each value is then read ~2(2r+1) times from shared memory
+// instead of L1 / L2); LAND_SEA stages the window of both planes.
 constexpr int kCircTW = 64;
 
-__global__ void __launch_bounds__(256) circ_gather_tiled_kernel(const CircGlobalParams p, int TH, int tiles_x,
-                                                                int tiles_y) {
+template <typename PT, bool LS, bool PW>
+__global__ void __launch_bounds__(256)
+circ_gather_tiled_kernel(const CircGlobalParams p, const __grid_constant__ CircWidths cw, int TH, int tiles_x,
+                         int tiles_y) {
+  if (p.guarded && *p.guard == 0) return;
+  typedef typename CircAcc<PT>::acc_t acc_t;
   extern __shared__ __align__(16) unsigned char smem_c[];
   const int r = p.r;
   const int TC = kCircTW + 2 * r + 1, TR = TH + 2 * r;
-  double* tile = reinterpret_cast<double*>(smem_c);            // [TR][TC], col j <-> global col x0 - r - 1 + j
-  int* wtab_s = reinterpret_cast<int*>(tile + (size_t)TR * TC);
-  for (int k = threadIdx.x; k <= r; k += blockDim.x) wtab_s[k] = p.wtab[k];
+  PT* tile = reinterpret_cast<PT*>(smem_c);            // [LS ? 2 : 1][TR][TC], col j <-> global col x0 - r - 1 + j
 
   long long bid = blockIdx.x;
   const int tx = (int)(bid % tiles_x); bid /= tiles_x;
@@ -370,14 +438,18 @@ __global__ void __launch_bounds__(256) circ_gather_tiled_kernel(const CircGlobal
   const int b = (int)bid;
   const int x0 = tx * kCircTW, y0 = ty * TH;
   const long long per_plane = (long long)p.ny * p.nx;
-  const double* pre = p.prefix + (long long)b * per_plane;
-#pragma unroll 8
-  for (int i = threadIdx.x; i < TR * TC; i += blockDim.x) {
-    const int jr = i / TC, jc = i - jr * TC;
-    const int ys = min(max(y0 - r + jr, 0), p.ny - 1);          // edge replication in y
-    const int gc = x0 - r - 1 + jc;
-    if (p.flags & NBH_WRAP_X) tile[i] = wrap_prefix(pre + (long long)ys * p.nx, gc, p.nx);
-    else tile[i] = gc < 0 ? 0.0 : pre[(long long)ys * p.nx + min(gc, p.nx - 1)];
+#pragma unroll
+  for (int k = 0; k < (LS ? 2 : 1); ++k) {
+    const PT* pre = reinterpret_cast<const PT*>(k ? p.prefix2 : p.prefix) + (long long)b * per_plane;
+    PT* tl = tile + (size_t)k * TR * TC;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < TR * TC; i += blockDim.x) {
+      const int jr = i / TC, jc = i - jr * TC;
+      const int ys = min(max(y0 - r + jr, 0), p.ny - 1);          // edge replication in y
+      const int gc = x0 - r - 1 + jc;
+      if (p.flags & NBH_WRAP_X) tl[i] = wrap_prefix<PT>(pre + (long long)ys * p.nx, gc, p.nx);
+      else tl[i] = gc < 0 ? (PT)0 : pre[(long long)ys * p.nx + min(gc, p.nx - 1)];
+    }
   }
   __syncthreads();
 
@@ -389,67 +461,86 @@ __global__ void __launch_bounds__(256) circ_gather_tiled_kernel(const CircGlobal
   for (int ly = threadIdx.x / kCircTW; ly < TH; ly += blockDim.x / kCircTW) {
     const int y = y0 + ly;
     if (y >= p.ny) break;
-    double S = 0.0;
+    const long long pt = (long long)y * p.nx + x;
+    const PT* tl = tile + ((LS && p.mask2d[pt] == 0) ? (size_t)TR * TC : 0);
+    acc_t S = 0;
     if ((p.flags & NBH_WRAP_X) || (x - r - 1 >= -1 && x + r <= p.nx - 1)) {
       // every span lies inside the row (or the axis is periodic): two loads and two adds per kernel row
-      const double* row = tile + (size_t)ly * TC + cshift + x;
-      for (int dy = -r; dy <= r; ++dy) {
-        const int w = wtab_s[dy < 0 ? -dy : dy];
-        S += row[w] - row[-w - 1];
+      const PT* row = tl + (size_t)ly * TC + cshift + x;
+#pragma unroll 4
+      for (int dy = 0; dy <= 2 * r; ++dy) {
+        const int w = PW ? (int)cw.w[dy] : p.wtab[dy < r ? r - dy : dy - r];
+        S += (acc_t)(PT)(row[w] - row[-w - 1]);
         row += TC;
       }
     } else {
       for (int dy = -r; dy <= r; ++dy) {
-        const int w = wtab_s[dy < 0 ? -dy : dy];
-        const double* row = tile + (size_t)(ly + r + dy) * TC + cshift;   // indexable by global column >= -1
+        const int w = PW ? (int)cw.w[dy + r] : p.wtab[dy < 0 ? -dy : dy];
+        const PT* row = tl + (size_t)(ly + r + dy) * TC + cshift;   // indexable by global column >= -1
         const int lo = max(x - w, 0), hi = min(x + w, p.nx - 1);
-        double s = row[hi] - row[lo - 1];
+        PT s = row[hi] - row[lo - 1];
         const int nl = lo - (x - w), nr = (x + w) - hi;             // replicated edge cells (mode="nearest")
-        if (nl > 0) s += (double)nl * (row[0] - row[-1]);
-        if (nr > 0) s += (double)nr * (row[p.nx - 1] - row[p.nx - 2]);
-        S += s;
+        if (nl > 0) s += (PT)nl * (row[0] - row[-1]);
+        if (nr > 0) s += (PT)nr * (row[p.nx - 1] - row[p.nx - 2]);
+        S += (acc_t)s;
       }
     }
-    const long long pt = (long long)y * p.nx + x;
-    const long long o = (plane * p.n_thr + p.t) * per_plane + pt;
-    float res;
-    if (p.flags & NBH_SUM_ONLY) {
-      res = (float)S;
-    } else {
-      const float Af = p.mask2d ? p.area[pt] : p.area_const;
-      res = (Af == 0.f) ? __int_as_float(0x7fc00000) : (float)(S / (double)Af * p.inv_members);
-    }
-    p.out[o] = res;
-    if (p.out_mask) p.out_mask[o] = (p.mask2d && p.mask2d[pt] == 0) ? 1 : 0;
+    circ_store<PT>(p, S, 0.0, false, plane, pt, per_plane);
   }
 }
 
-// pick the tallest tile that fits; 0 = use the direct (L2) gather
-static int circ_tile_rows(int r, int nx, size_t* smem) {
-  // measured on B200: the tile pays off while it is small enough for several blocks per SM
-  if (nx < 3 || r > env_int("NBH_CIRC_TILED_MAX_R", 16)) return 0;
-  for (int th : {64, 32, 16, 8}) {
-    const size_t bytes = (size_t)(th + 2 * r) * (kCircTW + 2 * r + 1) * 8 + (size_t)(r + 1) * 4 + 16;
-    if (bytes <= (th >= 32 ? 100u : 200u) * 1024) { *smem = bytes; return th; }
+// pick the tallest tile that fits; 0 = use the direct gather
+static int circ_tile_rows(int r, int nx, size_t elem, int n_tiles, size_t* smem) {
+  if (nx < 3) return 0;
+  for (int th : {64, 32, 16}) {
+    const size_t bytes = (size_t)n_tiles * (th + 2 * r) * (kCircTW + 2 * r + 1) * elem;
+    // worth it while a few blocks fit on an SM and the staged window is well reused
+    if (bytes <= 72u * 1024 && (size_t)(th + 2 * r) * (kCircTW + 2 * r + 1) <= (size_t)12 * th * kCircTW) {
+      *smem = bytes;
+      return th;
+    }
   }
   return 0;
 }
 
-static int launch_circ_gather(const CircGlobalParams& g, int ny, int nx, cudaStream_t st) {
+template <typename PT, bool LS, bool PW>
+static int launch_circ_gather_t(const CircGlobalParams& g, const CircWidths& cw, int ny, int nx, bool allow_tile,
+                                cudaStream_t st) {
   size_t smem = 0;
-  const int th = (g.cprefix || env_int("NBH_CIRC_TILED", 1) == 0) ? 0 : circ_tile_rows(g.r, nx, &smem);
+  const int th = (g.cprefix || !allow_tile) ? 0 : circ_tile_rows(g.r, nx, sizeof(PT), LS ? 2 : 1, &smem);
   if (th > 0) {
-    NBH_CHECK_CUDA(cudaFuncSetAttribute(circ_gather_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
+    auto kern = circ_gather_tiled_kernel<PT, LS, PW>;
+    NBH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles_x = (nx + kCircTW - 1) / kCircTW, tiles_y = (ny + th - 1) / th;
     const long long blocks = (long long)tiles_x * tiles_y * g.n_batch;
     NBH_REQUIRE(blocks < (1LL << 31), "too many blocks");
-    circ_gather_tiled_kernel<<<(unsigned)blocks, 256, smem, st>>>(g, th, tiles_x, tiles_y);
+    kern<<<(unsigned)blocks, 256, smem, st>>>(g, cw, th, tiles_x, tiles_y);
   } else {
     const long long outs = (long long)g.n_batch * ny * nx;
-    circ_gather_kernel<<<(unsigned)((outs + 255) / 256), 256, (size_t)(g.r + 1) * 4, st>>>(g);
+    circ_gather_kernel<PT, LS, PW><<<(unsigned)((outs + 255) / 256), 256, 0, st>>>(g, cw);
   }
   return 0;
+}
+
+template <typename PT>
+static int launch_circ_pass(const CircGlobalParams& g, const CircWidths& cw, int ny, int nx, bool allow_tile,
+                            cudaStream_t st) {
+  const bool ls = (g.flags & NBH_LAND_SEA) != 0, pw = g.r <= kCircParamRadius;
+  const long long rows = (long long)g.n_batch * ny;
+  const unsigned pgrid = (unsigned)((rows + 7) / 8);
+  if (ls) circ_prefix_kernel<PT, true><<<pgrid, 256, 0, st>>>(g);
+  else circ_prefix_kernel<PT, false><<<pgrid, 256, 0, st>>>(g);
+  if (ls) return pw ? launch_circ_gather_t<PT, true, true>(g, cw, ny, nx, allow_tile, st)
+                    : launch_circ_gather_t<PT, true, false>(g, cw, ny, nx, allow_tile, st);
+  return pw ? launch_circ_gather_t<PT, false, true>(g, cw, ny, nx, allow_tile, st)
+            : launch_circ_gather_t<PT, false, false>(g, cw, ny, nx, allow_tile, st);
+}
+
+// area of the own surface type from the land area: land points keep A_land, sea points get
+// sum(K) - A_land
+__global__ void circ_area_own_kernel(float* area, const uint8_t* land, float area_const, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && land[i] == 0) area[i] = area_const - area[i];
 }
 
 // area_sum for an external mask at large radius, from the prefix of the mask itself
@@ -463,13 +554,14 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr int kCircSmemMaxRadius = 40;          // beyond this the global-prefix path is used
 constexpr size_t kCircPrefixBudget = 256u << 20;  // bytes of float64 prefixes per batch (L2-friendly)
 
-int env_int(const char* name, int dflt);
-// unweighted discs: global-prefix gather from radius NBH_CIRC_GLOBAL_MIN_R upwards
+// unweighted discs use the prefix + gather path at every radius (measured on B200: it beats the
+// shared-memory ring kernel from radius 1); weighted discs the ring kernel
 static bool use_global_path(const NbhDesc& d) {
   if (d.cells > kCircSmemMaxRadius) return true;
-  if (d.flags & NBH_WEIGHTED) return false;
-  return d.cells >= env_int("NBH_CIRC_GLOBAL_MIN_R", 1);   // measured on B200: wins at every radius
+  return !(d.flags & NBH_WEIGHTED);
 }
+
+bool circular_native_land_sea(const NbhDesc& d) { return use_global_path(d) && !(d.flags & NBH_WEIGHTED); }
 
 struct CircWorkspace {
   double* ktab;
@@ -477,8 +569,10 @@ struct CircWorkspace {
   float* area_const;
   float* area;
   double* prefix;
+  double* prefix2;
   double* cprefix;
   float* maskf;
+  int* guard;
   int batch;
   size_t total;
 };
@@ -491,7 +585,8 @@ static void carve(const NbhDesc& d, void* ws, CircWorkspace* w) {
   w->wtab = reinterpret_cast<int*>(base + off); off = align_up(off + (r + 1) * 4, 256);
   w->area_const = reinterpret_cast<float*>(base + off); off = align_up(off + 4, 256);
   w->area = reinterpret_cast<float*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 4, 256);
-  w->prefix = w->cprefix = nullptr; w->maskf = nullptr; w->batch = 0;
+  w->guard = reinterpret_cast<int*>(base + off); off = align_up(off + 4, 256);
+  w->prefix = w->prefix2 = w->cprefix = nullptr; w->maskf = nullptr; w->batch = 0;
   if (use_global_path(d)) {
     const size_t per_plane = (size_t)d.ny * d.nx * 8;
     long long batch = (long long)(kCircPrefixBudget / per_plane);
@@ -500,6 +595,7 @@ static void carve(const NbhDesc& d, void* ws, CircWorkspace* w) {
     w->batch = (int)batch;
     w->prefix = reinterpret_cast<double*>(base + off); off = align_up(off + per_plane * batch, 256);
     if (d.mask_nd) { w->cprefix = reinterpret_cast<double*>(base + off); off = align_up(off + per_plane * batch, 256); }
+    if (d.flags & NBH_LAND_SEA) { w->prefix2 = reinterpret_cast<double*>(base + off); off = align_up(off + per_plane * batch, 256); }
     w->maskf = reinterpret_cast<float*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 4, 256);
   }
   w->total = off;
@@ -513,7 +609,6 @@ size_t circular_workspace_bytes(const NbhDesc& d) {
 
 int validate_desc(const NbhDesc* d);
 int fill_thresholds(const NbhDesc& d, ThrSet* ts, int* tm);
-int env_int(const char* name, int dflt);
 
 template <int TM, bool MASKND, bool WEIGHTED>
 static int launch_circ(const CircParams& p, int tx, size_t smem, long long blocks, cudaStream_t st) {
@@ -548,36 +643,56 @@ int run_circular(const NbhDesc* d, const float* in, float* out, uint8_t* out_mas
 
   if (use_global_path(*d)) {
     NBH_REQUIRE(!weighted, "weighted_mode is limited to radii of at most %d grid cells", kCircSmemMaxRadius);
+    const bool land_sea = (d->flags & NBH_LAND_SEA) != 0;
+    const bool sum_only = (d->flags & NBH_SUM_ONLY) != 0;
     CircGlobalParams g;
     memset(&g, 0, sizeof(g));
     ThrSet ts;
     int tm = 0;
     if (fill_thresholds(*d, &ts, &tm)) return 1;
     g.in = in; g.out = out; g.out_mask = out_mask; g.mask2d = d->mask2d; g.mask_nd = d->mask_nd;
-    g.area = w.area; g.wtab = w.wtab; g.prefix = w.prefix; g.cprefix = w.cprefix; g.status = status;
+    g.area = w.area; g.wtab = w.wtab; g.prefix = w.prefix; g.prefix2 = w.prefix2; g.cprefix = w.cprefix;
+    g.status = status; g.guard = w.guard;
     g.plane_stride = d->plane_stride; g.member_stride = d->member_stride;
     g.n_members = d->n_members; g.ny = d->ny; g.nx = d->nx; g.r = r; g.flags = d->flags;
     g.n_thr = max(d->n_thresholds, 1);
-    g.inv_members = (d->flags & NBH_SUM_ONLY) ? 1.0 : 1.0 / (double)d->n_members;
+    g.inv_members = sum_only ? 1.0 : 1.0 / (double)d->n_members;
+    g.fx_scale = 1.f; g.fx_inv = 1.0;
+    CircWidths cw;
+    memset(&cw, 0, sizeof(cw));
     {
       double tot = 0.0;
-      for (int dy = -r; dy <= r; ++dy) tot += 2.0 * floor(sqrt((double)(r * r - dy * dy))) + 1.0;
+      const long long r2 = (long long)r * r;
+      for (int dy = -r; dy <= r; ++dy) {
+        long long wdt = (long long)floor(sqrt((double)(r2 - (long long)dy * dy)));
+        while ((wdt + 1) * (wdt + 1) + (long long)dy * dy <= r2) ++wdt;
+        while (wdt > 0 && wdt * wdt + (long long)dy * dy > r2) --wdt;
+        tot += 2.0 * (double)wdt + 1.0;
+        if (r <= kCircParamRadius) cw.w[dy + r] = (short)wdt;
+      }
       g.area_const = (float)tot;
     }
+    // fixed-point prefixes: span differences stay below 2^32
+    int fx_shift = 0;
+    while (fx_shift < 24 && (double)nb * d->n_members * (double)(1u << (fx_shift + 1)) < 4294967296.0) ++fx_shift;
+    const bool fx_ok = !masknd && !sum_only && fx_shift >= 16;
     NBH_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int32_t), st));
+    NBH_CHECK_CUDA(cudaMemsetAsync(w.guard, 0, sizeof(int), st));
     circ_tables_kernel<<<1, 256, 0, st>>>(w.ktab, w.wtab, w.area_const, r, 0);
     const long long npts = (long long)d->ny * d->nx;
-    if (d->mask2d && !masknd && !(d->flags & NBH_SUM_ONLY)) {
-      // area_sum = the same gather applied to the mask (one plane, sum_only)
+    if (d->mask2d && !masknd && !sum_only) {
+      // area_sum = the same gather applied to the mask (one plane of 0 / 1, exact in fixed point)
       circ_mask_to_float_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(d->mask2d, w.maskf, npts);
       CircGlobalParams a = g;
       a.in = w.maskf; a.out = w.area; a.out_mask = nullptr; a.mask2d = nullptr; a.mask_nd = nullptr;
-      a.cprefix = nullptr; a.plane_stride = npts; a.member_stride = 0; a.n_members = 1; a.n_thr = 1; a.t = 0;
-      a.plane0 = 0; a.n_batch = 1; a.flags = NBH_SUM_ONLY | (d->flags & NBH_WRAP_X); a.thr.mode = 0;
-      circ_prefix_kernel<<<(unsigned)((d->ny + 7) / 8), 256, 0, st>>>(a);
-      if (launch_circ_gather(a, d->ny, d->nx, st)) return 1;
+      a.cprefix = nullptr; a.prefix2 = nullptr; a.plane_stride = npts; a.member_stride = 0; a.n_members = 1;
+      a.n_thr = 1; a.t = 0; a.plane0 = 0; a.n_batch = 1; a.flags = NBH_SUM_ONLY | (d->flags & NBH_WRAP_X);
+      a.thr.mode = 0; a.inv_members = 1.0;
+      if (launch_circ_pass<unsigned>(a, cw, d->ny, d->nx, true, st)) return 1;
+      if (land_sea)
+        circ_area_own_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(w.area, d->mask2d, g.area_const, npts);
     }
-    ProfileScope prof(st);
+    ProfileScope prof(st, "nbh::circ_prefix_kernel + nbh::circ_gather_kernel (row-span decomposition)");
     for (int t = 0; t < g.n_thr; ++t) {
       g.t = t;
       g.thr = ts.t[d->n_thresholds ? t : 0];
@@ -585,9 +700,15 @@ int run_circular(const NbhDesc* d, const float* in, float* out, uint8_t* out_mas
       for (long long p0 = 0; p0 < d->n_planes; p0 += w.batch) {
         g.plane0 = p0;
         g.n_batch = (int)min((long long)w.batch, d->n_planes - p0);
-        const long long rows = (long long)g.n_batch * d->ny;
-        circ_prefix_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(g);
-        if (launch_circ_gather(g, d->ny, d->nx, st)) return 1;
+        if (fx_ok) {
+          CircGlobalParams f = g;
+          f.fx_scale = (float)(1u << fx_shift); f.fx_inv = 1.0 / (double)(1u << fx_shift);
+          f.check_range = d->n_thresholds == 0 ? 1 : 0;      // raw data: speculative, verified by the pass itself
+          if (launch_circ_pass<unsigned>(f, cw, d->ny, d->nx, true, st)) return 1;
+          if (!f.check_range) continue;
+          g.guarded = 1;                                       // float64 re-run only if a value left [0, 1]
+        }
+        if (launch_circ_pass<double>(g, cw, d->ny, d->nx, true, st)) return 1;
       }
     }
     NBH_CHECK_CUDA(cudaGetLastError());
@@ -607,7 +728,6 @@ int run_circular(const NbhDesc* d, const float* in, float* out, uint8_t* out_mas
               "circular neighbourhood radius of %d cells does not fit in shared memory", r);
   // prefer smaller blocks when the radius is small (more blocks per SM)
   if (r <= 12 && tx > 128) tx = 128;
-  tx = env_int("NBH_CIRC_TX", tx);
 
   CircParams p;
   memset(&p, 0, sizeof(p));
@@ -625,11 +745,8 @@ int run_circular(const NbhDesc* d, const float* in, float* out, uint8_t* out_mas
   p.n_thr = max(d->n_thresholds, 1);
   p.inv_members = (d->flags & NBH_SUM_ONLY) ? 1.0 : 1.0 / (double)d->n_members;
   const long long tiles_xy = (long long)p.n_strips * d->n_planes * p.n_thr;
-  int ysegs = env_int("NBH_CIRC_YSEGS", 0);
-  if (ysegs <= 0) {
-    const long long want = 4LL * sm_count() * 2;
-    ysegs = (int)max(1LL, min((long long)d->ny / max(16, 4 * r), (want + tiles_xy - 1) / tiles_xy));
-  }
+  const long long want = 4LL * sm_count() * 2;
+  int ysegs = (int)max(1LL, min((long long)d->ny / max(16, 4 * r), (want + tiles_xy - 1) / tiles_xy));
   ysegs = max(1, min(ysegs, d->ny));
   p.seg_rows = (d->ny + ysegs - 1) / ysegs;
   p.n_ysegs = (d->ny + p.seg_rows - 1) / p.seg_rows;

@@ -51,11 +51,12 @@ __device__ __forceinline__ float load_value(const SqParams& p, long long plane, 
 
 template <int TM>
 __global__ void __launch_bounds__(256)
-square_stats_kernel(const SqParams p, int chunks, const int* suspects, const int* n_suspects) {
- const long long n_work = (long long)(*n_suspects) * chunks;
+square_stats_kernel(const SqParams p, int chunks, const int* suspects, const int* n_suspects, long long n_all) {
+ // suspects == nullptr: every one of the n_all slices
+ const long long n_work = (suspects ? (long long)(*n_suspects) : n_all) * chunks;
  for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
   const int chunk = (int)(work % chunks);
-  const long long sidx = suspects[work / chunks];
+  const long long sidx = suspects ? suspects[work / chunks] : work / chunks;
   long long bid = sidx;
   const int t = (int)(bid % p.n_thr); bid /= p.n_thr;
   const int m = (int)(bid % p.n_members);
@@ -68,7 +69,8 @@ square_stats_kernel(const SqParams p, int chunks, const int* suspects, const int
        pt += (long long)chunks * blockDim.x) {
     bool valid, seen; float tv;
     float v = load_value<TM>(p, plane, m, thr, pt, &valid, &seen, &tv);
-    const int y = (int)(pt / p.nx), x = (int)(pt - (long long)y * p.nx);
+    const int yl = (int)(pt / p.nx), x = (int)(pt - (long long)yl * p.nx);
+    const int y = yl + p.y_offset;                         // row of the whole grid
     if (v != 0.f) { b[0] = min(b[0], y); b[1] = max(b[1], y); b[2] = min(b[2], x); b[3] = max(b[3], x); }
     if (v != 1.f) { b[4] = min(b[4], y); b[5] = max(b[5], y); b[6] = min(b[6], x); b[7] = max(b[7], x); }
     if (seen && !__isnanf(tv)) { int k = float_key(tv); kmin = min(kmin, k); kmax = max(kmax, k); }
@@ -101,22 +103,24 @@ __device__ __forceinline__ long long grown_area(int ymin, int ymax, int xmin, in
 
 template <int TM>
 __global__ void __launch_bounds__(256)
-square_fixup_kernel(const SqParams p, int chunks, const int* suspects, const int* n_suspects) {
- const long long n_work = (long long)(*n_suspects) * chunks;
+square_fixup_kernel(const SqParams p, int chunks, const int* suspects, const int* n_suspects, long long n_all,
+                    const SliceStats* stats) {
+ const long long n_work = (suspects ? (long long)(*n_suspects) : n_all) * chunks;
  for (long long work = blockIdx.x; work < n_work; work += gridDim.x) {
   const int chunk = (int)(work % chunks);
-  const long long sidx = suspects[work / chunks];
+  const long long sidx = suspects ? suspects[work / chunks] : work / chunks;
   long long bid = sidx;
   const int t = (int)(bid % p.n_thr); bid /= p.n_thr;
   const int m = (int)(bid % p.n_members);
   const long long plane = bid / p.n_members;
-  const SliceStats s = p.stats[sidx];
+  const SliceStats s = stats[sidx];
   const int h = p.r;
-  long long size = (long long)p.ny * p.nx;
+  const int NYG = p.ny_global;                             // the boxes live in the rows of the whole grid
+  long long size = (long long)NYG * p.nx;
   int e = 0, ya, yb, xa, xb, y1a, y1b, x1a, x1b;
-  long long a0 = grown_area(s.y0min, s.y0max, s.x0min, s.x0max, h, p.ny, p.nx, &ya, &yb, &xa, &xb);
+  long long a0 = grown_area(s.y0min, s.y0max, s.x0min, s.x0max, h, NYG, p.nx, &ya, &yb, &xa, &xb);
   if (a0 < size) { size = a0; e = 0; }
-  long long a1 = grown_area(s.y1min, s.y1max, s.x1min, s.x1max, h, p.ny, p.nx, &y1a, &y1b, &x1a, &x1b);
+  long long a1 = grown_area(s.y1min, s.y1max, s.x1min, s.x1max, h, NYG, p.nx, &y1a, &y1b, &x1a, &x1b);
   if (a1 < size) { size = a1; e = 1; }
   if (e != 1 || size == 0) continue;
   if (chunk == 0 && threadIdx.x == 0) atomicAdd(p.status + 1, 1);
@@ -124,11 +128,16 @@ square_fixup_kernel(const SqParams p, int chunks, const int* suspects, const int
   const float vmin = key_float(s.vmin_key), vmax = key_float(s.vmax_key);
   const bool wrap = (p.flags & NBH_WRAP_X) != 0;
   const int bw = x1b - x1a;
+  // rows of the box this band owns (a y-band leaves its halo rows to the neighbouring band)
+  y1a = max(y1a, p.y_offset + p.halo_top);
+  y1b = min(y1b, p.y_offset + p.ny - p.halo_bottom);
+  if (y1b <= y1a) continue;
   const long long nbox = (long long)(y1b - y1a) * bw;
   for (long long q = (long long)chunk * blockDim.x + threadIdx.x; q < nbox;
        q += (long long)chunks * blockDim.x) {
-    const int y = y1a + (int)(q / bw), x = x1a + (int)(q % bw);
-    const int wy0 = max(y - h, 0), wy1 = min(y + h, p.ny - 1);
+    const int yg = y1a + (int)(q / bw), x = x1a + (int)(q % bw);
+    const int y = yg - p.y_offset;                         // local row
+    const int wy0 = max(yg - h, 0) - p.y_offset, wy1 = min(yg + h, NYG - 1) - p.y_offset;
     const int rows_in = wy1 - wy0 + 1;
     const int cols_in = wrap ? p.nb : (min(x + h, p.nx - 1) - max(x - h, 0) + 1);
     const int n_out = p.nb * p.nb - rows_in * cols_in;
@@ -168,9 +177,9 @@ __global__ void collect_suspects_kernel(const unsigned* flags, long long n, int*
 __global__ void init_stats_kernel(unsigned* flags, SliceStats* stats, long long n, unsigned init_bits,
                                   int* n_suspects) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) *n_suspects = 0;
+  if (i == 0 && n_suspects) *n_suspects = 0;
   if (i >= n) return;
-  flags[i] = init_bits;
+  if (flags) flags[i] = init_bits;
   SliceStats s;
   s.y0min = s.x0min = s.y1min = s.x1min = INT_MAX;
   s.y0max = s.x0max = s.y1max = s.x1max = -1;
@@ -373,6 +382,8 @@ size_t square_workspace_bytes(const NbhDesc& d) {
   return w.total;
 }
 
+bool square_native_land_sea(const NbhDesc&) { return false; }
+
 int validate_desc(const NbhDesc* d) {
   NBH_REQUIRE(d != nullptr, "null descriptor");
   NBH_REQUIRE(d->ny > 0 && d->nx > 0 && d->n_planes > 0, "empty grid (%d x %d, %lld planes)", d->ny,
@@ -384,6 +395,21 @@ int validate_desc(const NbhDesc* d) {
               "n_thresholds must be in [0, %d], got %d", kMaxThresholds, d->n_thresholds);
   NBH_REQUIRE(d->n_thresholds == 0 || d->thresholds != nullptr, "thresholds pointer is null");
   NBH_REQUIRE(!(d->mask_nd && d->n_members != 1), "mask_nd requires n_members == 1");
+  NBH_REQUIRE(!(d->flags & NBH_LAND_SEA) || (d->mask2d && !d->mask_nd),
+              "NBH_LAND_SEA needs the land mask as mask2d and no masked-array input");
+  if (d->ny_global != 0) {
+    NBH_REQUIRE(d->y_offset >= 0 && d->y_offset + d->ny <= d->ny_global,
+                "band rows [%d, %d) do not lie inside the grid of %d rows", d->y_offset, d->y_offset + d->ny,
+                d->ny_global);
+    NBH_REQUIRE(d->halo_top >= 0 && d->halo_bottom >= 0 && d->halo_top + d->halo_bottom < d->ny,
+                "halo rows (%d + %d) leave no own rows in a band of %d rows", d->halo_top, d->halo_bottom, d->ny);
+    NBH_REQUIRE((d->y_offset == 0 || d->halo_top >= d->cells) &&
+                (d->y_offset + d->ny == d->ny_global || d->halo_bottom >= d->cells),
+                "a band needs at least `cells` halo rows on every side that is not a domain edge");
+  } else {
+    NBH_REQUIRE(d->y_offset == 0 && d->halo_top == 0 && d->halo_bottom == 0,
+                "y_offset / halo rows given without ny_global");
+  }
   return 0;
 }
 
@@ -405,6 +431,8 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   if (validate_desc(d)) return 1;
   NBH_REQUIRE(in && out && status && workspace, "null pointer argument");
   NBH_REQUIRE(workspace_bytes >= square_workspace_bytes(*d), "workspace too small");
+  NBH_REQUIRE(d->ny_global == 0 || d->ext_stats != nullptr || (d->flags & NBH_SUM_ONLY),
+              "y-band launches need the statistics of the whole slices (ext_stats)");
   const bool masknd = d->mask_nd != nullptr;
   SqPlan pl;
   if (plan_square(*d, masknd, &pl)) return 1;
@@ -429,6 +457,8 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   p.cpl_magic = (65536 + p.cpl - 1) / p.cpl;
   p.inv_members = 1.0 / (double)d->n_members;
   if (d->flags & NBH_SUM_ONLY) p.inv_members = 1.0;   // a sum is never averaged
+  p.y_offset = d->y_offset; p.ny_global = d->ny_global ? d->ny_global : d->ny;
+  p.halo_top = d->halo_top; p.halo_bottom = d->halo_bottom;
 
   const long long nslices = d->n_planes * d->n_members * p.n_thr;
   const bool sum_only = (d->flags & NBH_SUM_ONLY) != 0;
@@ -507,7 +537,7 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   long long tile_blocks = 0;
   size_t tile_smem = 0;
   const bool use_tile = !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && !use_tma && !use_mt &&
-                        plan_square_tile(*d, in, &tlg, &tile_blocks, &tile_smem);
+                        !(d->flags & NBH_EXACT_SUMS) && plan_square_tile(*d, in, &tlg, &tile_blocks, &tile_smem);
   SqRsGeom rg;
   int rs_grid = 0;
   const bool use_rs = !use_tile && use_warp && !use_tma && !use_mt && plan_square_rs(*d, in, &rg, &rs_grid);
@@ -564,27 +594,66 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   }
   if (rc) return rc;
   if (!sum_only) {
-    // trimming fix-up: nothing to do (three tiny launches) unless a slice is suspicious
     const int chunks = 32;
+    const unsigned fb = (unsigned)min((long long)sm_count() * 8, nslices * chunks);
+    if (d->ext_stats) {
+      // y-band launch: the bounding boxes and the extremes of the WHOLE slices come from the caller
+      // (nbh_slice_stats_f32 on every band + all-reduce); every slice is looked at
+      switch (tm) {
+        case 0: square_fixup_kernel<0><<<fb, 256, 0, st>>>(p, chunks, nullptr, nullptr, nslices, d->ext_stats); break;
+        case 1: square_fixup_kernel<1><<<fb, 256, 0, st>>>(p, chunks, nullptr, nullptr, nslices, d->ext_stats); break;
+        default: square_fixup_kernel<2><<<fb, 256, 0, st>>>(p, chunks, nullptr, nullptr, nslices, d->ext_stats); break;
+      }
+      NBH_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
+    // trimming fix-up: nothing to do (three tiny launches) unless a slice is suspicious
     collect_suspects_kernel<<<(unsigned)((nslices + 255) / 256), 256, 0, st>>>(w.edge_flags, nslices,
                                                                             w.suspects, w.n_suspects);
-    const unsigned fb = (unsigned)min((long long)sm_count() * 8, nslices * chunks);
     switch (tm) {
       case 0:
-        square_stats_kernel<0><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects);
-        square_fixup_kernel<0><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects);
+        square_stats_kernel<0><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects, 0);
+        square_fixup_kernel<0><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects, 0, w.stats);
         break;
       case 1:
-        square_stats_kernel<1><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects);
-        square_fixup_kernel<1><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects);
+        square_stats_kernel<1><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects, 0);
+        square_fixup_kernel<1><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects, 0, w.stats);
         break;
       default:
-        square_stats_kernel<2><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects);
-        square_fixup_kernel<2><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects);
+        square_stats_kernel<2><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects, 0);
+        square_fixup_kernel<2><<<fb, 256, 0, st>>>(p, chunks, w.suspects, w.n_suspects, 0, w.stats);
         break;
     }
     NBH_CHECK_CUDA(cudaGetLastError());
   }
+  return 0;
+}
+
+// nbh_slice_stats_f32: the statistics of every slice of a band, rows in grid coordinates
+int run_slice_stats(const NbhDesc* d, const float* in, NbhSliceStats* stats, cudaStream_t st) {
+  if (validate_desc(d)) return 1;
+  NBH_REQUIRE(in && stats, "null pointer argument");
+  SqParams p;
+  memset(&p, 0, sizeof(p));
+  int tm = 0;
+  if (fill_thresholds(*d, &p.thr, &tm)) return 1;
+  p.in = in; p.mask2d = d->mask2d; p.mask_nd = d->mask_nd; p.stats = stats;
+  p.plane_stride = d->plane_stride; p.member_stride = d->member_stride;
+  p.n_planes = d->n_planes; p.n_members = d->n_members;
+  p.ny = d->ny; p.nx = d->nx; p.r = d->cells; p.nb = 2 * d->cells + 1; p.flags = d->flags;
+  p.n_thr = max(d->n_thresholds, 1);
+  p.y_offset = d->y_offset; p.ny_global = d->ny_global ? d->ny_global : d->ny;
+  const long long nslices = d->n_planes * d->n_members * p.n_thr;
+  NBH_REQUIRE(nslices < (1LL << 31), "too many slices in one launch (%lld)", nslices);
+  init_stats_kernel<<<(unsigned)((nslices + 255) / 256), 256, 0, st>>>(nullptr, stats, nslices, 0u, nullptr);
+  const int chunks = 32;
+  const unsigned fb = (unsigned)min((long long)sm_count() * 8, nslices * chunks);
+  switch (tm) {
+    case 0: square_stats_kernel<0><<<fb, 256, 0, st>>>(p, chunks, nullptr, nullptr, nslices); break;
+    case 1: square_stats_kernel<1><<<fb, 256, 0, st>>>(p, chunks, nullptr, nullptr, nslices); break;
+    default: square_stats_kernel<2><<<fb, 256, 0, st>>>(p, chunks, nullptr, nullptr, nslices); break;
+  }
+  NBH_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -5,11 +5,9 @@
 
 namespace nbh {
 
-struct SliceStats {      // exact per-slice statistics, only built for suspicious slices
-  int y0min, y0max, x0min, x0max;   // bbox of v != 0
-  int y1min, y1max, x1min, x1max;   // bbox of v != 1
-  int vmin_key, vmax_key;           // ordered-int keys of nanmin / nanmax of the slice
-};
+// exact per-slice statistics (bounding boxes of v != 0 / v != 1, nanmin / nanmax keys): built
+// lazily for suspicious slices, or handed in by the caller for y-band tiled launches
+using SliceStats = NbhSliceStats;
 
 struct SqParams {
   const float* in;
@@ -29,6 +27,8 @@ struct SqParams {
   int W, WS, hl, n_strips, n_ysegs, seg_rows;
   int n_thr;                 // max(n_thresholds, 1)
   int cpl, cpl_magic;        // columns per lane in the horizontal pass, ceil(65536 / cpl)
+  int y_offset, ny_global;   // y-band tiling: global row of local row 0, rows of the whole grid (ny if not tiled)
+  int halo_top, halo_bottom; // rows of the band that are halo (outputs not needed)
   double inv_members;
   ThrSet thr;
 };

@@ -7,7 +7,6 @@ all arithmetic happens in libimprover_b200.so through the C ABI
 """
 from __future__ import annotations
 
-import contextlib
 import os
 
 import ctypes as C
@@ -22,21 +21,16 @@ from ._lib import NbhDesc, NbhThreshold
 MAX_THRESHOLDS_PER_LAUNCH = 8
 NAN_MESSAGE = "Error: NaN detected in input cube data"   # nbhood.py:168, threshold.py:665
 
-_workspaces = {}
-
-
 def _require_cuda(t: torch.Tensor, name: str) -> None:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise TypeError(f"{name} must be a CUDA tensor (improver_b200 has no CPU path)")
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
-    return ws
+    """Scratch for one native call, taken from PyTorch's caching allocator: blocks are reused in
+    stream order, so concurrent streams never share one, and a call captured into a CUDA graph
+    gets its block from the graph's private pool (it stays valid for every replay)."""
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
 def _stream_ptr() -> int:
@@ -62,21 +56,34 @@ def check_status(status: torch.Tensor) -> int:
     return fixed
 
 
-@contextlib.contextmanager
-def exact_square_sums():
-    """Within this context single-member square launches use the kernels with exact window sums
-    (float64 / fixed point: `square_rs_kernel` rows mode and the warp / block kernels) instead of
-    the float32 running sums of `square_tile_kernel`.  Their results do not depend on where a tile
-    starts, so a y-band of a grid reproduces the rows of the whole grid bit for bit."""
-    old = os.environ.get("NBH_SQ_TILE")
-    os.environ["NBH_SQ_TILE"] = "0"
-    try:
-        yield
-    finally:
-        if old is None:
-            del os.environ["NBH_SQ_TILE"]
-        else:
-            os.environ["NBH_SQ_TILE"] = old
+class Band:
+    """Position of a y-band inside its grid (NbhDesc.y_offset / ny_global / halo_top /
+    halo_bottom): the launch sees rows [y_offset, y_offset + rows) of `ny_global`, of which the
+    first `halo_top` and the last `halo_bottom` came from the neighbouring bands."""
+
+    def __init__(self, y_offset: int, ny_global: int, halo_top: int = 0, halo_bottom: int = 0):
+        self.y_offset, self.ny_global = int(y_offset), int(ny_global)
+        self.halo_top, self.halo_bottom = int(halo_top), int(halo_bottom)
+
+
+def _fill_desc(data, cells, flags, n_planes, n_members, ny, nx, plane_stride, member_stride, thr_arr, T,
+               mask2d, mask_nd, plane_cells=None, band: Optional[Band] = None, ext_stats=None):
+    desc = NbhDesc()
+    desc.n_planes, desc.n_members, desc.ny, desc.nx = n_planes, n_members, ny, nx
+    desc.cells = int(cells)
+    desc.plane_stride, desc.member_stride = plane_stride, member_stride
+    desc.flags = flags
+    desc.n_thresholds = T
+    desc.thresholds = thr_arr if T else None
+    desc.mask2d = mask2d.data_ptr() if mask2d is not None else None
+    desc.mask_nd = mask_nd.data_ptr() if mask_nd is not None else None
+    if plane_cells is not None:
+        desc.plane_cells = plane_cells.ctypes.data_as(C.POINTER(C.c_int32))
+    if band is not None:
+        desc.y_offset, desc.ny_global = band.y_offset, band.ny_global
+        desc.halo_top, desc.halo_bottom = band.halo_top, band.halo_bottom
+    desc.ext_stats = ext_stats.data_ptr() if ext_stats is not None else None
+    return desc
 
 
 def neighbourhood(
@@ -92,6 +99,11 @@ def neighbourhood(
     wrap_x: bool = False,
     want_mask: bool = False,
     out: Optional[torch.Tensor] = None,
+    exact: bool = False,
+    land_sea: bool = False,
+    plane_cells: Optional[Sequence[int]] = None,
+    band: Optional[Band] = None,
+    ext_stats: Optional[torch.Tensor] = None,
 ):
     """Neighbourhood sum/mean of every 2-D slice of `data`.
 
@@ -103,6 +115,13 @@ def neighbourhood(
     thresholds      optional sequence of (value, lo, hi, op): the fuzzy
                     threshold is applied to each value first and a threshold
                     axis is inserted before (ny, nx).
+    exact           single-member square launches: kernels whose window sums do not depend
+                    on where a tile / band starts (NBH_EXACT_SUMS).
+    land_sea        mask2d is a land mask; every point is normalised over the points of its
+                    own surface type (NBH_LAND_SEA: land pass + sea pass + sum in one launch).
+    plane_cells     one radius (grid cells) per plane instead of `cells` (lead-time radii).
+    band, ext_stats y-band tiling: position of this band in its grid and the int32 (slices, 10)
+                    statistics of the whole slices (slice_stats on every band + all-reduce).
     Returns (out, out_mask or None, status).  status is an int32[2] CUDA
     tensor; pass it to check_status() (this is the only synchronisation).
     """
@@ -164,6 +183,22 @@ def neighbourhood(
         flags |= _lib.WRAP_X
     if weighted_mode:
         flags |= _lib.WEIGHTED
+    if exact:
+        flags |= _lib.EXACT_SUMS
+    if land_sea:
+        if mask2d is None:
+            raise ValueError("land_sea needs the land mask as mask2d")
+        flags |= _lib.LAND_SEA
+    pc = None
+    if plane_cells is not None:
+        pc = np.ascontiguousarray(np.asarray(list(plane_cells), dtype=np.int32))
+        if pc.shape != (n_planes,):
+            raise ValueError(f"plane_cells must hold one radius per plane ({n_planes})")
+    if ext_stats is not None:
+        _require_cuda(ext_stats, "ext_stats")
+        if ext_stats.dtype != torch.int32 or not ext_stats.is_contiguous() or \
+                ext_stats.numel() != n_planes * n_members * max(len(list(thresholds or [])), 1) * 10:
+            raise ValueError("ext_stats must be a contiguous int32 (slices, 10) tensor")
     if method == "square":
         fn = lib.nbh_square_f32
     elif method == "circular":
@@ -171,20 +206,12 @@ def neighbourhood(
     else:
         raise ValueError("{} is not a valid neighbourhood_method.".format(method))
 
-    desc = NbhDesc()
-    desc.n_planes, desc.n_members, desc.ny, desc.nx = n_planes, n_members, ny, nx
-    desc.cells = int(cells)
-    desc.plane_stride, desc.member_stride = slice_elems, member_stride
-    desc.flags = flags
-    desc.mask2d = mask2d.data_ptr() if mask2d is not None else None
-    desc.mask_nd = mask_nd.data_ptr() if mask_nd is not None else None
-
     stream = _stream_ptr()
     with torch.cuda.device(data.device):
         if T <= MAX_THRESHOLDS_PER_LAUNCH:
             thr_arr = make_thresholds(thr_list) if T else None
-            desc.n_thresholds = T
-            desc.thresholds = thr_arr if T else None
+            desc = _fill_desc(data, cells, flags, n_planes, n_members, ny, nx, slice_elems, member_stride,
+                              thr_arr, T, mask2d, mask_nd, pc, band, ext_stats)
             ws = _workspace(data.device, lib.nbh_workspace_bytes(C.byref(desc)))
             _lib.check(fn(C.byref(desc), data.data_ptr(), out.data_ptr(),
                           out_mask.data_ptr() if want_mask else None, status.data_ptr(),
@@ -195,15 +222,66 @@ def neighbourhood(
             acc_status = torch.zeros(2, dtype=torch.int32, device=data.device)
             for t0 in range(0, T, MAX_THRESHOLDS_PER_LAUNCH):
                 chunk = thr_list[t0:t0 + MAX_THRESHOLDS_PER_LAUNCH]
+                sub_stats = None
+                if ext_stats is not None:
+                    sub_stats = ext_stats.view(-1, T, 10)[:, t0:t0 + len(chunk)].contiguous()
                 sub, sub_mask, st = neighbourhood(
                     data, cells, method, mask2d, mask_nd, weighted_mode, sum_only, chunk,
-                    collapse_members, wrap_x, want_mask)
+                    collapse_members, wrap_x, want_mask, None, exact, land_sea, plane_cells, band, sub_stats)
                 out[..., t0:t0 + len(chunk), :, :] = sub
                 if want_mask:
                     out_mask[..., t0:t0 + len(chunk), :, :] = sub_mask
                 acc_status = torch.maximum(acc_status, st)
             status = acc_status
     return out, out_mask, status
+
+
+def slice_stats(data: torch.Tensor, cells: int, mask2d: Optional[torch.Tensor] = None,
+                mask_nd: Optional[torch.Tensor] = None, thresholds=None, collapse_members: bool = False,
+                band: Optional[Band] = None) -> torch.Tensor:
+    """Per-slice statistics int32 (slices, 10) of `data` as neighbourhood() would see it (after
+    thresholding and masking): bounding boxes of the values != 0 and != 1 (rows in grid
+    coordinates when `band` is given) and nanmin / nanmax keys.  Columns 0, 2, 4, 6, 8 combine
+    across bands with MIN, columns 1, 3, 5, 7, 9 with MAX (nbhood.py:252-256, 353-382)."""
+    lib = _lib.load()
+    _require_cuda(data, "data")
+    if data.dtype != torch.float32 or data.dim() < 2:
+        raise TypeError("data must be float32 with (y, x) axes")
+    data = data.contiguous()
+    ny, nx = int(data.shape[-2]), int(data.shape[-1])
+    lead = tuple(int(s) for s in data.shape[:-2])
+    if collapse_members:
+        n_members, plane_shape = lead[0], lead[1:]
+    else:
+        n_members, plane_shape = 1, lead
+    n_planes = int(np.prod(plane_shape)) if plane_shape else 1
+    thr_list = list(thresholds) if thresholds is not None else []
+    T = len(thr_list)
+    if T > MAX_THRESHOLDS_PER_LAUNCH:
+        raise ValueError(f"at most {MAX_THRESHOLDS_PER_LAUNCH} thresholds per call")
+    if mask2d is not None:
+        mask2d = (mask2d != 0).to(torch.uint8).contiguous()
+    if mask_nd is not None:
+        mask_nd = (mask_nd != 0).to(torch.uint8).contiguous()
+    thr_arr = make_thresholds(thr_list) if T else None
+    desc = _fill_desc(data, cells, 0, n_planes, n_members, ny, nx, ny * nx,
+                      n_planes * ny * nx if collapse_members else 0, thr_arr, T, mask2d, mask_nd, None, band)
+    stats = torch.empty((n_planes * n_members * max(T, 1), 10), dtype=torch.int32, device=data.device)
+    with torch.cuda.device(data.device):
+        _lib.check(lib.nbh_slice_stats_f32(C.byref(desc), data.data_ptr(), stats.data_ptr(), _stream_ptr()))
+    return stats
+
+
+def neighbourhood_land_sea(data: torch.Tensor, cells: int, land_mask: torch.Tensor, method: str = "square",
+                           weighted_mode: bool = False, sum_only: bool = False, thresholds=None,
+                           collapse_members: bool = False, plane_cells=None):
+    """Land points neighbourhooded over land points only, sea points over sea points only, both in
+    one launch (the land pass + sea pass + filled(0) sum of cli/nbhood_land_and_sea.py:148-184).
+    land_mask uint8/bool (ny, nx), non-zero = land.  Returns (out, status)."""
+    out, _, status = neighbourhood(data, cells, method=method, mask2d=land_mask, weighted_mode=weighted_mode,
+                                   sum_only=sum_only, thresholds=thresholds, collapse_members=collapse_members,
+                                   land_sea=True, plane_cells=plane_cells)
+    return out, status
 
 
 def threshold(data: torch.Tensor, thresholds, mask_nd: Optional[torch.Tensor] = None,

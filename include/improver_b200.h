@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NBH_ABI_VERSION 1
+#define NBH_ABI_VERSION 2
 
 /* comparison operators, improver/utilities/probability_manipulation.py:15-66 */
 enum { NBH_OP_GT = 0, NBH_OP_GE = 1, NBH_OP_LT = 2, NBH_OP_LE = 3, NBH_OP_EQ = 4 };
@@ -35,7 +35,12 @@ enum { NBH_OP_GT = 0, NBH_OP_GE = 1, NBH_OP_LT = 2, NBH_OP_LE = 3, NBH_OP_EQ = 4
 enum {
   NBH_SUM_ONLY = 1,   /* NeighbourhoodProcessing(sum_only=True), nbhood.py:188 */
   NBH_WRAP_X   = 2,   /* extension: periodic x (global grids); no reference parity */
-  NBH_WEIGHTED = 4    /* circular weighted_mode, nbhood.py:55-92 */
+  NBH_WEIGHTED = 4,   /* circular weighted_mode, nbhood.py:55-92 */
+  NBH_EXACT_SUMS = 8, /* single-member square launches: only kernels whose window sums do not depend on
+                         where a tile / band starts (a y-band then reproduces the whole grid bit for bit) */
+  NBH_LAND_SEA = 16   /* mask2d is a land mask (non-zero = land): every point is normalised over the points
+                         of its OWN surface type, i.e. the land pass + sea pass + filled(0) sum of
+                         improver/cli/nbhood_land_and_sea.py:148-184 in one launch (re_mask is implied) */
 };
 
 /* One threshold with its fuzzy bounds (improver/threshold.py:302-333).
@@ -72,12 +77,70 @@ typedef struct NbhDesc {
   const uint8_t* mask2d;    /* (ny,nx) non-zero = valid point (mask_cube, nbhood.py:453-456) or NULL */
   const uint8_t* mask_nd;   /* same shape as input, non-zero = MASKED (np.ma mask) or NULL;
                                requires n_members == 1 */
+  /* --- ABI 2 --- */
+  const int32_t* plane_cells;  /* HOST array of n_planes radii in grid cells (lead-time dependent radii,
+                                  nbhood.py:132-149 / 438-455: one radius per slice) or NULL: `cells` for all */
+  /* y-band tiling of one huge grid: this launch sees rows
+   * [y_offset, y_offset + ny) of a grid of ny_global rows.  The band must include the halo rows it
+   * received from its neighbours; `halo_top` / `halo_bottom` of its first / last rows are such
+   * halo rows (their outputs are not produced).  ny_global == 0: not tiled. */
+  int32_t y_offset;
+  int32_t ny_global;
+  int32_t halo_top;
+  int32_t halo_bottom;
+  /* per-slice statistics of the WHOLE grid (nbh_slice_stats_f32 on every band + min / max
+   * all-reduce), n_planes * n_members * max(n_thresholds, 1) entries, DEVICE pointer; required
+   * when ny_global != 0 and the launch is not sum_only (the reference's clip and its trimming
+   * bounding boxes, nbhood.py:252-256 / 341-409, are properties of the whole slice) */
+  const struct NbhSliceStats* ext_stats;
 } NbhDesc;
+
+/* Exact statistics of one 2-D slice after thresholding / masking (10 x int32).  The *min fields
+ * combine across bands with MIN, the *max fields with MAX. */
+typedef struct NbhSliceStats {
+  int32_t y0min, y0max, x0min, x0max;   /* bounding box of values != 0 (rows global: + y_offset) */
+  int32_t y1min, y1max, x1min, x1max;   /* bounding box of values != 1 */
+  int32_t vmin_key, vmax_key;           /* nanmin / nanmax of the slice as ordered-int keys:
+                                           key = bits >= 0 ? bits : bits ^ 0x7fffffff */
+} NbhSliceStats;
 
 int nbh_version(void);
 const char* nbh_last_error(void);
 /* number of SMs and opt-in shared memory of the current device */
 int nbh_device_info(int32_t* sm_count, int64_t* smem_optin_bytes);
+
+/* Per-slice statistics of a band (or of a whole grid): slice index
+ * (plane * n_members + member) * max(n_thresholds, 1) + threshold.  Replaces the per-slice
+ * nanmin / nanmax and np.argwhere bounding boxes of improver/nbhood/nbhood.py:252-256, 353-382. */
+int nbh_slice_stats_f32(const NbhDesc* desc, const float* in, NbhSliceStats* stats, void* stream);
+
+/* y-band tiling, the data movement of the halo exchange that does not need a communicator:
+ * the rows a band sends to its neighbours / receives from them are packed into / unpacked from
+ * contiguous buffers, so that the exchange itself is one ncclSend / ncclRecv pair per neighbour
+ * (the caller owns the communicator: torch.distributed in improver_b200.distributed, or
+ * ncclGroupStart(); ncclSend(send_up..); ncclRecv(recv_up..); ... ncclGroupEnd() from C).
+ *   band      float32 (n_slices, rows, nx): own rows of every slice
+ *   ext       float32 (n_slices, halo_top + rows + halo_bottom, nx): the extended band
+ *   nbh_halo_pack:   send_up   <- first `cells` rows of every slice (n_slices, cells, nx) or NULL
+ *                    send_down <- last  `cells` rows                                   or NULL
+ *                    and copies the own rows into ext
+ *   nbh_halo_unpack: ext top halo <- recv_up (n_slices, halo_top, nx), bottom halo <- recv_down */
+int nbh_halo_pack(const float* band, float* ext, float* send_up, float* send_down, int64_t n_slices,
+                  int32_t rows, int32_t nx, int32_t cells, int32_t halo_top, int32_t halo_bottom,
+                  void* stream);
+int nbh_halo_unpack(float* ext, const float* recv_up, const float* recv_down, int64_t n_slices,
+                    int32_t rows, int32_t nx, int32_t halo_top, int32_t halo_bottom, void* stream);
+
+/* The whole exchange in one stream-ordered call: pack, one ncclSend / ncclRecv pair per
+ * neighbouring rank inside one NCCL group (NVLink / NVSwitch, no host staging), unpack.
+ *   nccl_comm  the caller's ncclComm_t (ranks ordered top band = 0 ... bottom band = n_ranks - 1)
+ *   ext        float32 (n_slices, halo_top + rows + halo_bottom, nx) with halo_top = rank > 0 ? cells : 0,
+ *              halo_bottom = rank < n_ranks - 1 ? cells : 0
+ * NCCL is resolved at run time from the library already loaded into the process. */
+size_t nbh_halo_exchange_workspace_bytes(int64_t n_slices, int32_t nx, int32_t cells);
+int nbh_halo_exchange(void* nccl_comm, int32_t rank, int32_t n_ranks, const float* band, float* ext,
+                      int64_t n_slices, int32_t rows, int32_t nx, int32_t cells, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* Scratch the caller must provide (zero-initialisation not required). */
 size_t nbh_workspace_bytes(const NbhDesc* desc);

@@ -21,15 +21,44 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
     assert set(_lib.EXPORTED) == declared
-    assert _lib.load().nbh_version() == 1
+    assert _lib.load().nbh_version() == 2
 
 
 def test_struct_layout_matches_header():
     from improver_b200._lib import NbhDesc, NbhThreshold
 
     assert ctypes.sizeof(NbhThreshold) == 32
-    assert ctypes.sizeof(NbhDesc) == 72
+    assert ctypes.sizeof(NbhDesc) == 104
     assert NbhDesc.thresholds.offset == 48 and NbhDesc.mask2d.offset == 56
+    assert NbhDesc.plane_cells.offset == 72 and NbhDesc.y_offset.offset == 80 and NbhDesc.ext_stats.offset == 96
+    from improver_b200._lib import NbhSliceStats
+    assert ctypes.sizeof(NbhSliceStats) == 40
+
+
+def test_struct_layout_agrees_with_the_compiler(tmp_path):
+    """sizeof / offsetof of the header's structs as gcc sees them."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "improver_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(NbhDesc), offsetof(NbhDesc, plane_cells),'
+                   'offsetof(NbhDesc, y_offset), offsetof(NbhDesc, ext_stats), sizeof(NbhSliceStats), sizeof(NbhThreshold));return 0;}')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(v) for v in out] == [104, 72, 80, 96, 40, 32]
+
+
+def test_counter_based_generator_is_sharding_independent():
+    """workloads.counter_uniform (config 5 input): torch == numpy restatement, and a shard
+    reproduces its part of the whole."""
+    import torch
+    from improver_b200 import workloads as W
+
+    whole = W.counter_uniform(0, 5, (12, 20), 5, "cpu").numpy()
+    np.testing.assert_array_equal(whole, W.counter_uniform_host(0, 5, (12, 20), 5))
+    part = W.counter_uniform(3, 2, (12, 20), 5, "cpu").numpy()
+    np.testing.assert_array_equal(part, whole[3:5])
+    assert 0.0 <= whole.min() and whole.max() < 1.0 and abs(whole.mean() - 0.5) < 0.05
 
 
 def test_no_cpu_fallback_without_cuda():
