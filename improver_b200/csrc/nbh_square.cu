@@ -15,6 +15,7 @@
 #include "nbh_square_mt.cuh"
 #include "nbh_square_tma.cuh"
 #include "nbh_square_rs.cuh"
+#include "nbh_square_box.cuh"
 
 namespace nbh {
 
@@ -358,6 +359,7 @@ struct SqWorkspace {
   double* rcp_count;
   float* cnt_plane;
   uint16_t* tmp;
+  void* box;
   size_t total;
 };
 
@@ -373,6 +375,8 @@ static void carve_workspace(const NbhDesc& d, void* ws, SqWorkspace* w) {
   w->rcp_count = reinterpret_cast<double*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 8, 256);
   w->tmp = reinterpret_cast<uint16_t*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 2, 256);
   w->cnt_plane = reinterpret_cast<float*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 4, 256);
+  w->box = base + off;
+  if (d.n_members == 1) off = align_up(off + box_workspace_bytes((long long)nslices, d.ny, d.nx), 256);
   w->total = off;
 }
 
@@ -533,14 +537,51 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   const bool use_mt = !use_tma && use_warp && pl.vec >= 2 && d->n_members >= 2 && d->n_thresholds >= 2 &&
                       tm >= 1 && !(d->flags & NBH_WRAP_X) && env_int("NBH_SQ_MT", 0) &&   // opt-in: see profiles/r1_multi_threshold.jsonl
                       plan_square_warp(*d, 2, &wgm) && wgm.WS == 64;
+  // single-member slices: the fixed-point box kernel (radius <= 8 cells), its guarded follow-ups,
+  // and for raw data the guarded float64 re-run of slices that are not probabilities
+  SqBoxGeom bg;
+  int box_grid = 0;
+  size_t box_smem = 0;
+  const bool use_box = !masknd && !use_tma && !use_mt && env_int("NBH_SQ_BOX", 1) &&
+                       plan_square_box(*d, in, &bg, &box_grid, &box_smem);
   SqTileGeom tlg;
   long long tile_blocks = 0;
   size_t tile_smem = 0;
-  const bool use_tile = !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && !use_tma && !use_mt &&
+  const bool use_tile = !use_box && !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && !use_tma && !use_mt &&
                         !(d->flags & NBH_EXACT_SUMS) && plan_square_tile(*d, in, &tlg, &tile_blocks, &tile_smem);
   SqRsGeom rg;
   int rs_grid = 0;
-  const bool use_rs = !use_tile && use_warp && !use_tma && !use_mt && plan_square_rs(*d, in, &rg, &rs_grid);
+  const bool use_rs = !use_box && !use_tile && use_warp && !use_tma && !use_mt && plan_square_rs(*d, in, &rg, &rs_grid);
+  if (use_box) {
+    BoxWorkspace bw;
+    box_carve(w.box, nslices, d->ny, d->nx, &bw);
+    if (box_prepare(bw, d->mask2d, nslices, d->ny, d->nx, st)) return 1;
+    bg.stats = bw.stats; bg.maskf = bw.maskf;
+    {
+      ProfileScope prof(st, "nbh::square_box_kernel (row-streaming, fixed-point, shuffle windows)");
+      rc = launch_square_box(p, bg, tm_warp, d->mask2d != nullptr, box_grid, box_smem, st);
+    }
+    if (rc) return rc;
+    if (box_finish(bw, p, d->ext_stats, tm, nslices, st)) return 1;
+    if (tm == 0) {
+      SqParams pr = p;
+      pr.redo = bw.redo;
+      const bool m2d = d->mask2d != nullptr;
+      if (use_warp) {
+        switch (pl.vec) {
+          case 4: rc = launch_square_warp_vec<4>(pr, wg, tm_warp, m2d, st); break;
+          case 2: rc = launch_square_warp_vec<2>(pr, wg, tm_warp, m2d, st); break;
+          default: rc = launch_square_warp_vec<1>(pr, wg, tm_warp, m2d, st); break;
+        }
+      } else {
+        switch (pl.vec) {
+          case 4: rc = launch_square_vec<4>(pr, pl, blocks, tm, masknd, m2d, st); break;
+          case 2: rc = launch_square_vec<2>(pr, pl, blocks, tm, masknd, m2d, st); break;
+          default: rc = launch_square_vec<1>(pr, pl, blocks, tm, masknd, m2d, st); break;
+        }
+      }
+    }
+  } else
   if (use_tile) {
     ProfileScope prof(st, "nbh::square_tile_kernel (separable running sums in independent tiles)");
     rc = launch_square_tile(p, tlg, tm_warp, d->mask2d != nullptr, tile_blocks, tile_smem, st);

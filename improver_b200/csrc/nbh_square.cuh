@@ -18,6 +18,8 @@ struct SqParams {
   const double* rcp_count;   // (ny,nx) 1/count for mask2d launches
   const float* cnt_plane;    // (ny,nx) the count itself (float32), same launches
   int32_t* status;
+  const int* redo;           // not NULL: only the units (plane * T + t) flagged here are computed (guarded
+                             // float64 re-run of the slices the fixed-point box kernel could not take)
   unsigned* edge_flags;      // [(plane*R + m) * T + t]
   SliceStats* stats;
   long long plane_stride, member_stride;
@@ -184,6 +186,7 @@ square_kernel(const __grid_constant__ SqParams p) {
   const int yseg = (int)(bid % p.n_ysegs); bid /= p.n_ysegs;
   const int t = (int)(bid % p.n_thr); bid /= p.n_thr;
   const long long plane = bid;
+  if (p.redo && !p.redo[plane * p.n_thr + t]) return;
   const ThrDev thr = p.thr.t[TM ? t : 0];
 
   const int ya = yseg * p.seg_rows;

@@ -1,0 +1,516 @@
+// Square neighbourhood of single-member slices (NeighbourhoodProcessing.process itself,
+// improver/nbhood/nbhood.py:244-317 + boxsum, improver/utilities/neighbourhood_tools.py:129-211):
+// row-streaming box kernel with register-resident horizontal windows.
+//
+// One persistent block per SM slot owns a contiguous share of the (slice, y) rows.  Producer
+// threads stream batches of B rows into a ring of shared-memory stages with bulk asynchronous
+// copies (cp.async.bulk / mbarrier, as square_rs_kernel); every consumer warp owns a window of
+// 256 columns, EIGHT consecutive columns per lane, and marches down the rows:
+//
+//   vertical window  : the (thresholded, masked) values are turned into exact fixed point
+//                      (q = v * 2^s, round to nearest) and each lane keeps the running column
+//                      sums V += q_new - q_old of its eight columns in registers; the last 2r+1
+//                      quantised rows live in a warp-private shared-memory ring (16-byte
+//                      accesses, conflict free);
+//   horizontal window: compile-time radius R <= 8: a lane needs the column sums of columns
+//                      x0-R .. x0+7+R, i.e. its own eight, the last R of its left neighbour and
+//                      the first R of its right neighbour: 2R warp shuffles, then one 2R+1-term
+//                      sum and seven sliding updates (IADD3) — no scan, no prefix row, no
+//                      barrier.  Lane 0 and lane 31 of a window are halo lanes (240 useful
+//                      columns per window);
+//   normalise        : S / (rows_in * cols_in) as a correctly rounded float32 quotient
+//                      (reciprocal + two FMAs), or S / count[y][x] for an external mask.
+//
+// Unsigned 32-bit arithmetic throughout: (2r+1)^2 * 2^s < 2^32, so window sums are exact for the
+// quantised values whatever row a share or a y-band starts at (bit-identical bands), a window of
+// ones gives exactly 1 and a window of zeros exactly 0.  The quantisation contributes at most
+// 2^-(s+1) (3e-8 for r = 5) to a mean.  Raw slices are processed on the assumption that they are
+// probabilities in [0, 1]; the kernel records the extremes of every slice and of its results, and
+// the host queues (device-side guarded) follow-ups: slices outside [0, 1] are recomputed by the
+// float64 kernels, slices whose results left [min, max] by the quantisation are clamped
+// (nbhood.py:312).
+#pragma once
+#include "nbh_square_rs.cuh"
+
+namespace nbh {
+
+constexpr int kBoxMaxWindows = 6;            // consumer warps per block (1536 columns per panel)
+constexpr int kBoxProducers = 1;         // one thread issues a bulk copy every ~500 cycles: a stage of B rows
+                                         // per 500 cycles is several times what the consumers can take
+constexpr int kBoxThreads = (kBoxMaxWindows + kBoxProducers) * 32;
+constexpr int kBoxK = 8;                     // columns per lane
+constexpr int kBoxWinCols = 32 * kBoxK;      // 256
+constexpr int kBoxUseful = 30 * kBoxK;       // 240: lanes 1..30 produce outputs
+constexpr int kBoxMaxStages = 8;
+constexpr int kBoxBPlain = 4, kBoxBMasked = 2;   // rows per stage / batch (masked launches stage a mask row per data row)
+
+// per-slice extremes recorded by the box kernel (ordered-int keys, see float_key)
+struct BoxStats {
+  int in_min, in_max;        // raw data (before the threshold; the truth value is monotone in it)
+  int out_min, out_max;      // results
+};
+
+struct SqBoxGeom {
+  int n_windows;        // consumer warps = windows per x panel
+  int n_panels;
+  int n_windows_total;
+  int B;                // rows per stage
+  int n_stages;
+  int contiguous;       // 1: a stage is ONE copy of B consecutive full rows (n_panels == 1)
+  int seg_pitch;        // floats per staged row segment (segmented staging), multiple of 4
+  int stage_floats;     // floats per stage (data rows, then the mask rows for M2D)
+  int mask_off;         // float offset of the mask rows inside a stage
+  long long rows_total; // n_units * n_panels * ny
+  long long share;
+  int fx_shift;
+  unsigned wait_ns;
+  BoxStats* stats;      // [n_units]
+  const float* maskf;   // (ny, nx) float 0 / 1 plane of mask2d (M2D)
+};
+
+__device__ __forceinline__ int box_float_key(float f) {
+  const int b = __float_as_int(f);
+  return b >= 0 ? b : b ^ 0x7fffffff;
+}
+
+__device__ __forceinline__ float max3_nan(float a, float b, float c) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ float max3f(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+__device__ __forceinline__ void lds_f4(unsigned addr, float* v) {
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(addr));
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+8];" : "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+
+template <int R, int TM, bool M2D>
+__global__ void __launch_bounds__(kBoxThreads, 2)
+square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
+  static_assert(R >= 1 && R <= 8, "compile-time radius of the shuffle window");
+  constexpr int K = kBoxK, B = M2D ? kBoxBMasked : kBoxBPlain, NB = 2 * R + 1;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int NS = g.n_stages, NW = g.n_windows;
+
+  // layout: stages | full[8] empty[8] | per consumer warp: ring [NB][256] u32
+  float* stages = reinterpret_cast<float*>(smem_raw);
+  const unsigned stage_bytes = (unsigned)g.stage_floats * 4u;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)NS * stage_bytes);
+  const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + kBoxMaxStages);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(full0 + 8 * s, kBoxProducers); mbar_init(empty0 + 8 * s, NW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();      // the only block-level barrier
+
+  const unsigned long long in_elem0 = reinterpret_cast<unsigned long long>(p.in) >> 2;
+  const unsigned long long mk_elem0 = M2D ? (reinterpret_cast<unsigned long long>(g.maskf) >> 2) : 0ull;
+  const int NBP = g.n_windows_total;
+
+  // ======================= producer warps =======================
+  if (warp >= NW) {
+    if (lane != 0) return;
+    const int pw = warp - NW;
+    const unsigned stage0 = smem_u32(stages);
+    int s = 0;
+    unsigned round = 0;
+    RsPieces pieces(g.share, g.rows_total, p.ny, 0);
+    pieces.g0 = (long long)blockIdx.x * g.share;
+    pieces.g1 = min(g.rows_total, pieces.g0 + g.share);
+    pieces.g = pieces.g0;
+    long long task; int ya, yb;
+    while (pieces.next(&task, &ya, &yb)) {
+      const long long unit = task / g.n_panels;
+      const int panel = (int)(task - unit * g.n_panels);
+      const long long plane = unit / p.n_thr;
+      const int y_lo = max(ya - R, 0), y_hi = min(yb - 1 + R, p.ny - 1);
+      const int n_in = y_hi - y_lo + 1;
+      const int gw0 = panel * NW, gw1 = min(gw0 + NW, NBP) - 1;
+      const int seg0 = max(gw0 * kBoxUseful - K, 0);
+      const int seg1 = min(p.nx, gw1 * kBoxUseful - K + kBoxWinCols);
+      const float* plane_ptr = p.in + plane * p.plane_stride + seg0;
+      const float* mask_ptr = M2D ? g.maskf + seg0 : nullptr;
+      for (int k = 0; k < n_in; k += B) {
+        const int n = min(B, n_in - k);
+        const int y0 = y_lo + k;
+        mbar_wait_hint(empty0 + 8 * s, (round & 1u) ^ 1u, g.wait_ns);
+        const unsigned dst0 = stage0 + (unsigned)s * stage_bytes;
+        if (g.contiguous) {
+          // one copy of n full rows (+ one for the mask rows); the producers take the stages in turn
+          if ((int)((round * (unsigned)NS + (unsigned)s) % kBoxProducers) == pw) {
+            const float* row = plane_ptr + (long long)y0 * p.nx;
+            const unsigned sh = (unsigned)(reinterpret_cast<unsigned long long>(row) & 15ull);
+            const unsigned bytes = (sh + (unsigned)(n * p.nx) * 4u + 15u) & ~15u;
+            unsigned total = bytes, mbytes = 0, msh = 0;
+            const float* mrow = nullptr;
+            if (M2D) {
+              mrow = mask_ptr + (long long)y0 * p.nx;
+              msh = (unsigned)(reinterpret_cast<unsigned long long>(mrow) & 15ull);
+              mbytes = (msh + (unsigned)(n * p.nx) * 4u + 15u) & ~15u;
+              total += mbytes;
+            }
+            mbar_expect_tx(full0 + 8 * s, total);
+            bulk_g2s(dst0, reinterpret_cast<const char*>(row) - sh, bytes, full0 + 8 * s);
+            if (M2D) bulk_g2s(dst0 + (unsigned)g.mask_off * 4u, reinterpret_cast<const char*>(mrow) - msh, mbytes,
+                              full0 + 8 * s);
+          } else {
+            mbar_arrive(full0 + 8 * s);
+          }
+        } else {
+          // one copy per row segment; producer pw issues rows pw, pw + 4, ...
+          unsigned total = 0;
+          for (int j = pw; j < n; j += kBoxProducers) {
+            const float* row = plane_ptr + (long long)(y0 + j) * p.nx;
+            const unsigned sh = (unsigned)(reinterpret_cast<unsigned long long>(row) & 15ull);
+            total += (sh + (unsigned)(seg1 - seg0) * 4u + 15u) & ~15u;
+            if (M2D) {
+              const float* mrow = mask_ptr + (long long)(y0 + j) * p.nx;
+              const unsigned msh = (unsigned)(reinterpret_cast<unsigned long long>(mrow) & 15ull);
+              total += (msh + (unsigned)(seg1 - seg0) * 4u + 15u) & ~15u;
+            }
+          }
+          if (total) mbar_expect_tx(full0 + 8 * s, total); else mbar_arrive(full0 + 8 * s);
+          for (int j = pw; j < n; j += kBoxProducers) {
+            const float* row = plane_ptr + (long long)(y0 + j) * p.nx;
+            const unsigned sh = (unsigned)(reinterpret_cast<unsigned long long>(row) & 15ull);
+            const unsigned bytes = (sh + (unsigned)(seg1 - seg0) * 4u + 15u) & ~15u;
+            bulk_g2s(dst0 + (unsigned)(j * g.seg_pitch) * 4u, reinterpret_cast<const char*>(row) - sh, bytes,
+                     full0 + 8 * s);
+            if (M2D) {
+              const float* mrow = mask_ptr + (long long)(y0 + j) * p.nx;
+              const unsigned msh = (unsigned)(reinterpret_cast<unsigned long long>(mrow) & 15ull);
+              const unsigned mbytes = (msh + (unsigned)(seg1 - seg0) * 4u + 15u) & ~15u;
+              bulk_g2s(dst0 + (unsigned)(g.mask_off + j * g.seg_pitch) * 4u,
+                       reinterpret_cast<const char*>(mrow) - msh, mbytes, full0 + 8 * s);
+            }
+          }
+        }
+        if (++s == NS) { s = 0; ++round; }
+      }
+    }
+    return;
+  }
+
+  // ======================= consumer warps =======================
+  unsigned* ring = reinterpret_cast<unsigned*>(bars + 2 * kBoxMaxStages) + (size_t)warp * NB * kBoxWinCols;
+  const unsigned ring_u32 = smem_u32(ring) + (unsigned)lane * (K * 4u);
+  const bool sum_only = (p.flags & NBH_SUM_ONLY) != 0;
+  const float fx_scale = (float)(1u << g.fx_shift);
+  const unsigned ONE = 1u << g.fx_shift;
+  const float fx_inv = 1.0f / fx_scale;
+  const unsigned stages_u32 = smem_u32(stages);
+  float nanacc = 0.f;
+  int s = 0;
+  unsigned parity = 0, bar = full0, st_addr = stages_u32;
+
+  RsPieces pieces(g.share, g.rows_total, p.ny, 0);
+  pieces.g0 = (long long)blockIdx.x * g.share;
+  pieces.g1 = min(g.rows_total, pieces.g0 + g.share);
+  pieces.g = pieces.g0;
+  long long task; int ya, yb;
+  while (pieces.next(&task, &ya, &yb)) {
+    const long long unit = task / g.n_panels;
+    const int panel = (int)(task - unit * g.n_panels);
+    const int gw = panel * NW + warp;                       // window index within the full row
+    const int gw0 = panel * NW;
+    const int seg0 = max(gw0 * kBoxUseful - K, 0);          // first staged column of the panel
+    const int x0 = gw * kBoxUseful - K + lane * K;          // first column of this lane
+    const bool win_active = gw < NBP;
+    // columns of this lane inside the domain; a lane that is not fully inside reads the nearest
+    // fully valid group instead (its values are then zeroed / excluded explicitly)
+    unsigned okbits = 0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) okbits |= (win_active && x0 + i >= 0 && x0 + i < p.nx) ? (1u << i) : 0u;
+    const bool lane_full = okbits == 0xffu;
+    const bool warp_edge = __any_sync(0xffffffffu, !lane_full);
+    const int x_ld = lane_full ? x0 : (x0 < 0 || !win_active ? seg0 : max(seg0, ((p.nx - K) & ~1)));
+    const int ld_shift = lane_full ? 0 : (x0 >= 0 && win_active ? x0 - x_ld : 0);   // partial lane: columns moved right by this
+    const bool out_lane = lane >= 1 && lane <= 30 && okbits != 0;
+    const bool band_l = !sum_only && okbits && x0 <= R;
+    const bool band_r = !sum_only && okbits && x0 + K - 1 >= p.nx - 1 - R;
+    const long long plane = unit / p.n_thr;
+    const int t = (int)(unit - plane * p.n_thr);
+    const ThrDev& thr = p.thr.t[TM ? t : 0];
+    const int n_rows = (yb - ya) + 2 * R;
+    const int y_first = ya - R;
+    const long long obase0 = unit * (long long)p.ny * p.nx;
+    const unsigned long long plane_elem0 = in_elem0 + (unsigned long long)(plane * p.plane_stride) + (unsigned long long)seg0;
+    const unsigned lane_col_b = (unsigned)(x_ld - seg0) * 4u;
+
+    // normalisation constants: interior lanes share the row's reciprocal, edge lanes keep per-column counts
+    float ncol[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const int xo = x0 + i;
+      ncol[i] = (float)(min(xo + R, p.nx - 1) - max(xo - R, 0) + 1);
+    }
+    const bool lane_interior = (x0 - R >= 0) && (x0 + K - 1 + R <= p.nx - 1);
+
+    // zero the ring (rows above the domain are zeros)
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(ring_u32 + (unsigned)q * (kBoxWinCols * 4u)), "r"(0u));
+      asm volatile("st.shared.v4.u32 [%0+16], {%1, %1, %1, %1};" ::"r"(ring_u32 + (unsigned)q * (kBoxWinCols * 4u)), "r"(0u));
+    }
+    unsigned V[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) V[i] = 0u;
+    int slot = 0;
+    float dmin = __int_as_float(0x7f800000), dmax = __int_as_float(0xff800000);
+    float omin = __int_as_float(0x7f800000), omax = __int_as_float(0xff800000);
+    unsigned ne_bits = 0;                                   // bit0 top, bit1 bottom, bit2 left, bit3 right
+    __syncwarp();
+
+    const int n_in_piece = min(yb - 1 + R, p.ny - 1) - max(ya - R, 0) + 1;
+    int consumed = 0;
+    int k = max(0, -y_first);                               // leading rows above the domain are zeros
+    while (k < n_rows) {
+      const int yy0 = y_first + k;
+      const bool has_data = yy0 < p.ny;
+      int nbr;
+      float d[B][K];
+      float mk[M2D ? B : 1][K];
+      if (has_data) {
+        nbr = min(B, n_in_piece - consumed);
+        mbar_wait_hint(bar, parity, g.wait_ns);
+        const unsigned long long e0 = plane_elem0 + (unsigned long long)((long long)yy0 * p.nx);
+        const unsigned long long m0 = M2D ? mk_elem0 + (unsigned long long)((long long)yy0 * p.nx + seg0) : 0ull;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+          if (j < nbr) {
+            unsigned off, moff = 0;
+            if (g.contiguous) {
+              off = (unsigned)(e0 & 3ull) * 4u + (unsigned)(j * p.nx) * 4u;
+              if (M2D) moff = (unsigned)(m0 & 3ull) * 4u + (unsigned)(j * p.nx) * 4u;
+            } else {
+              off = (unsigned)((e0 + (unsigned long long)(j * p.nx)) & 3ull) * 4u + (unsigned)(j * g.seg_pitch) * 4u;
+              if (M2D) moff = (unsigned)((m0 + (unsigned long long)(j * p.nx)) & 3ull) * 4u + (unsigned)(j * g.seg_pitch) * 4u;
+            }
+            lds_f4(st_addr + off + lane_col_b, &d[j][0]);
+            lds_f4(st_addr + off + lane_col_b + 16u, &d[j][4]);
+            if (M2D) {
+              lds_f4(st_addr + (unsigned)g.mask_off * 4u + moff + lane_col_b, &mk[j][0]);
+              lds_f4(st_addr + (unsigned)g.mask_off * 4u + moff + lane_col_b + 16u, &mk[j][4]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < K; ++i) { d[j][i] = 0.f; if (M2D) mk[j][i] = 0.f; }
+          }
+        }
+        consumed += nbr;
+        __syncwarp();                                       // every lane has read the stage
+        if (lane == 0) mbar_arrive(bar + 8 * kBoxMaxStages);
+        bar += 8; st_addr += stage_bytes;
+        if (++s == NS) { s = 0; parity ^= 1u; bar = full0; st_addr = stages_u32; }
+      } else {
+        nbr = min(B, n_rows - k);                           // rows below the domain: zeros
+#pragma unroll
+        for (int j = 0; j < B; ++j)
+#pragma unroll
+          for (int i = 0; i < K; ++i) { d[j][i] = 0.f; if (M2D) mk[j][i] = 0.f; }
+      }
+
+      // ---- quantise, vertical running sums (sequential over the rows of the batch) ----
+      unsigned Vs[B][K];
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        if (j < nbr) {
+          unsigned q[K];
+          if (has_data) {
+            if (!sum_only || TM == 0) {
+              // extremes of the raw data (NaN propagates through the maximum: nbhood.py:167-168)
+              dmax = max3_nan(dmax, d[j][0], d[j][1]); dmax = max3_nan(dmax, d[j][2], d[j][3]);
+              dmax = max3_nan(dmax, d[j][4], d[j][5]); dmax = max3_nan(dmax, d[j][6], d[j][7]);
+              dmin = min3f(dmin, d[j][0], d[j][1]); dmin = min3f(dmin, d[j][2], d[j][3]);
+              dmin = min3f(dmin, d[j][4], d[j][5]); dmin = min3f(dmin, d[j][6], d[j][7]);
+            } else {
+              nanacc = max3_nan(nanacc, d[j][0], d[j][1]); nanacc = max3_nan(nanacc, d[j][2], d[j][3]);
+              nanacc = max3_nan(nanacc, d[j][4], d[j][5]); nanacc = max3_nan(nanacc, d[j][6], d[j][7]);
+            }
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+              float tv = truth_value_sum<TM>(d[j][i], thr);
+              if (M2D) tv *= mk[j][i];
+              q[i] = __float2uint_rn(tv * fx_scale);
+            }
+            if (warp_edge && !lane_full) {
+              // a lane straddling the right edge loaded the last eight columns of the row instead:
+              // its column i sits at position i + ld_shift (2, 4 or 6) of the loaded group
+              if (okbits == 0u) {
+#pragma unroll
+                for (int i = 0; i < K; ++i) q[i] = 0u;
+              } else if (ld_shift == 2) {
+                q[0] = q[2]; q[1] = q[3]; q[2] = q[4]; q[3] = q[5]; q[4] = q[6]; q[5] = q[7]; q[6] = 0u; q[7] = 0u;
+              } else if (ld_shift == 4) {
+                q[0] = q[4]; q[1] = q[5]; q[2] = q[6]; q[3] = q[7]; q[4] = 0u; q[5] = 0u; q[6] = 0u; q[7] = 0u;
+              } else {
+                q[0] = q[6]; q[1] = q[7]; q[2] = 0u; q[3] = 0u; q[4] = 0u; q[5] = 0u; q[6] = 0u; q[7] = 0u;
+              }
+            }
+            const int yy = yy0 + j;
+            if (!sum_only && (yy <= R || yy >= p.ny - 1 - R || band_l || band_r)) {
+              unsigned ne = 0;
+#pragma unroll
+              for (int i = 0; i < K; ++i) {
+                const int xo = x0 + i;
+                const bool okc = (okbits >> i) & 1u;
+                const bool n1 = okc && q[i] != ONE;
+                if (n1) {
+                  if (yy <= R) ne |= 1u;
+                  if (yy >= p.ny - 1 - R) ne |= 2u;
+                  if (xo <= R) ne |= 4u;
+                  if (xo >= p.nx - 1 - R) ne |= 8u;
+                }
+              }
+              ne_bits |= ne;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < K; ++i) q[i] = 0u;
+          }
+          // ring exchange: V += q - ring[slot]; ring[slot] = q
+          const unsigned ra = ring_u32 + (unsigned)slot * (kBoxWinCols * 4u);
+          unsigned o[K];
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(ra));
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]) : "r"(ra));
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]) : "memory");
+          asm volatile("st.shared.v4.u32 [%0+16], {%1, %2, %3, %4};" ::"r"(ra), "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7]) : "memory");
+#pragma unroll
+          for (int i = 0; i < K; ++i) { V[i] += q[i] - o[i]; Vs[j][i] = V[i]; }
+          slot = (slot + 1 == NB) ? 0 : slot + 1;
+        } else {
+#pragma unroll
+          for (int i = 0; i < K; ++i) Vs[j][i] = 0u;
+        }
+      }
+
+      // ---- horizontal windows from the neighbours' column sums, normalise, store ----
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        if (j < nbr && k + j >= 2 * R) {                    // warp-uniform
+          unsigned E[K + 2 * R];
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            E[i] = __shfl_up_sync(0xffffffffu, Vs[j][K - R + i], 1);
+            E[K + R + i] = __shfl_down_sync(0xffffffffu, Vs[j][i], 1);
+          }
+#pragma unroll
+          for (int i = 0; i < K; ++i) E[R + i] = Vs[j][i];
+          unsigned H[K];
+          unsigned acc = E[0];
+#pragma unroll
+          for (int c = 1; c <= 2 * R; ++c) acc += E[c];
+          H[0] = acc;
+#pragma unroll
+          for (int i = 1; i < K; ++i) H[i] = H[i - 1] + E[i + 2 * R] - E[i - 1];
+          if (out_lane) {
+            const int yo = y_first + k + j - R;
+            const int rows_in = min(yo + R, p.ny - 1) - max(yo - R, 0) + 1;
+            const long long pt0 = (long long)yo * p.nx + x0;
+            float o[K];
+            if (sum_only) {
+#pragma unroll
+              for (int i = 0; i < K; ++i) o[i] = (float)H[i] * fx_inv;
+            } else if (M2D) {
+#pragma unroll
+              for (int i = 0; i < K; ++i) {
+                const float cnt = ((okbits >> i) & 1u) ? __ldg(p.cnt_plane + pt0 + i) : 1.f;
+                const float nf = cnt * fx_scale;
+                float rc;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(nf));
+                const float Sf = (float)H[i];
+                const float q0 = Sf * rc;
+                const float rem = __fmaf_rn(-q0, nf, Sf);
+                o[i] = cnt == 0.f ? __int_as_float(0x7fc00000) : __fmaf_rn(rem, rc, q0);
+              }
+            } else {
+              const float nrow = (float)rows_in * fx_scale;
+#pragma unroll
+              for (int i = 0; i < K; ++i) {
+                const float nf = nrow * (lane_interior ? (float)NB : ncol[i]);
+                float rc;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(nf));
+                const float Sf = (float)H[i];
+                const float q0 = Sf * rc;
+                const float rem = __fmaf_rn(-q0, nf, Sf);
+                o[i] = __fmaf_rn(rem, rc, q0);
+              }
+            }
+            if (lane_full) {
+              if (!sum_only) {
+                omax = max3f(omax, o[0], o[1]); omax = max3f(omax, o[2], o[3]);
+                omax = max3f(omax, o[4], o[5]); omax = max3f(omax, o[6], o[7]);
+                omin = min3f(omin, o[0], o[1]); omin = min3f(omin, o[2], o[3]);
+                omin = min3f(omin, o[4], o[5]); omin = min3f(omin, o[6], o[7]);
+              }
+              float* op = p.out + obase0 + pt0;
+              *reinterpret_cast<float2*>(op) = make_float2(o[0], o[1]);
+              *reinterpret_cast<float2*>(op + 2) = make_float2(o[2], o[3]);
+              *reinterpret_cast<float2*>(op + 4) = make_float2(o[4], o[5]);
+              *reinterpret_cast<float2*>(op + 6) = make_float2(o[6], o[7]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < K; ++i) {
+                if ((okbits >> i) & 1u) {
+                  if (!sum_only) { omax = fmaxf(omax, o[i]); omin = fminf(omin, o[i]); }
+                  p.out[obase0 + pt0 + i] = o[i];
+                }
+              }
+            }
+            if (p.out_mask) {
+#pragma unroll
+              for (int i = 0; i < K; ++i)
+                if ((okbits >> i) & 1u) p.out_mask[obase0 + pt0 + i] = (M2D && p.mask2d[pt0 + i] == 0) ? 1 : 0;
+            }
+          }
+        }
+      }
+      k += nbr;
+    }
+
+    // ---- per-slice flags and extremes ----
+    if (!sum_only) {
+      const unsigned bits = __reduce_or_sync(0xffffffffu, ne_bits);
+      if (lane == 0 && bits) atomicOr(p.edge_flags + (plane * p.n_thr + t), bits);
+    }
+    if (!sum_only || TM == 0) {
+      // NaN in dmax marks the launch; the keys of the finite extremes go to the slice record
+      if (__isnanf(dmax)) nanacc = dmax;
+      int kmin = __isnanf(dmin) ? INT_MAX : box_float_key(dmin), kmax = __isnanf(dmax) ? INT_MIN : box_float_key(dmax);
+      int komin = box_float_key(omin), komax = box_float_key(omax);
+      kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
+      komin = __reduce_min_sync(0xffffffffu, komin); komax = __reduce_max_sync(0xffffffffu, komax);
+      if (lane == 0) {
+        BoxStats* bs = g.stats + unit;
+        atomicMin(&bs->in_min, kmin); atomicMax(&bs->in_max, kmax);
+        atomicMin(&bs->out_min, komin); atomicMax(&bs->out_max, komax);
+      }
+    }
+  }
+  if (__any_sync(0xffffffffu, __isnanf(nanacc))) {
+    if (lane == 0) atomicOr(reinterpret_cast<unsigned*>(p.status), 1u);
+  }
+}
+
+struct BoxWorkspace {
+  BoxStats* stats;
+  int* redo;
+  int* clamp_list;
+  float2* range;
+  int* n_clamp;
+  int* n_redo;
+  float* maskf;
+};
+size_t box_workspace_bytes(long long n_units, int ny, int nx);
+void box_carve(void* ws, long long n_units, int ny, int nx, BoxWorkspace* w);
+int box_prepare(const BoxWorkspace& w, const uint8_t* mask2d, long long n_units, int ny, int nx, cudaStream_t st);
+int box_finish(const BoxWorkspace& w, const SqParams& p, const NbhSliceStats* ext, int tm, long long n_units,
+               cudaStream_t st);
+bool plan_square_box(const NbhDesc& d, const float* in, SqBoxGeom* g, int* grid, size_t* smem);
+int launch_square_box(const SqParams& p, const SqBoxGeom& g, int tm, bool m2d, int grid, size_t smem, cudaStream_t st);
+
+}  // namespace nbh

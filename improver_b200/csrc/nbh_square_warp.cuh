@@ -66,6 +66,7 @@ square_warp_kernel(const __grid_constant__ SqParams p, const SqWarpGeom g) {
   const int yseg = (int)(task % g.n_ysegs); task /= g.n_ysegs;
   const int t = (int)(task % p.n_thr); task /= p.n_thr;
   const long long plane = task;
+  if (p.redo && !p.redo[plane * p.n_thr + t]) return;
   const ThrDev thr = p.thr.t[TM ? t : 0];
 
   const bool wrap = (p.flags & NBH_WRAP_X) != 0;

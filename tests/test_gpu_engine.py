@@ -331,9 +331,10 @@ def test_single_member_kernels_match_oracle(shape, cells, wrap, monkeypatch):
         flat[-1] = 1.0
         flat[-1, 10:12, -3:] = 0.0
     mask = (rng.random(shape[-2:]) < 0.8).astype(np.uint8)
-    variants = {"rows": {"NBH_SQ_TILE": "0", "NBH_SQ_RS_ROWS": "1"},
-                "tile": {"NBH_SQ_TILE": "1", "NBH_SQ_RS_ROWS": "1"},
-                "warp": {"NBH_SQ_TILE": "0", "NBH_SQ_RS_ROWS": "0"}}
+    variants = {"box": {"NBH_SQ_BOX": "1", "NBH_SQ_TILE": "1", "NBH_SQ_RS_ROWS": "1"},
+                "rows": {"NBH_SQ_BOX": "0", "NBH_SQ_TILE": "0", "NBH_SQ_RS_ROWS": "1"},
+                "tile": {"NBH_SQ_BOX": "0", "NBH_SQ_TILE": "1", "NBH_SQ_RS_ROWS": "1"},
+                "warp": {"NBH_SQ_BOX": "0", "NBH_SQ_TILE": "0", "NBH_SQ_RS_ROWS": "0"}}
     for m in (None, mask):
         md = _dev(m) if m is not None else None
         for sum_only in (False, True):
