@@ -167,6 +167,8 @@ int run_threshold_vicinity(const float* in, const uint8_t* mask_nd, const uint8_
 int run_threshold(const float*, const uint8_t*, float*, int32_t*, const NbhThreshold*, int, long long,
                   long long, int32_t*, cudaStream_t);
 int run_slice_stats(const NbhDesc*, const float*, NbhSliceStats*, cudaStream_t);
+int run_collapse_mean(const float*, float*, long long, long long, cudaStream_t);
+int run_zone_collapse(const float*, const float*, float*, long long, int, long long, cudaStream_t);
 int run_halo_pack(const float*, float*, float*, float*, long long, int, int, int, int, int, cudaStream_t);
 int run_halo_unpack(float*, const float*, const float*, long long, int, int, int, int, cudaStream_t);
 size_t halo_exchange_workspace_bytes(long long, int, int);
@@ -352,6 +354,15 @@ int nbh_circular_f32(const NbhDesc* desc, const float* in, float* out, uint8_t* 
                                     static_cast<cudaStream_t>(stream));
   return nbh::dispatch_circular(desc, in, out, out_mask, status, workspace, workspace_bytes,
                                 static_cast<cudaStream_t>(stream));
+}
+
+int nbh_collapse_mean_f32(const float* in, float* out, int64_t n_collapse, int64_t n_points, void* stream) {
+  return nbh::run_collapse_mean(in, out, n_collapse, n_points, static_cast<cudaStream_t>(stream));
+}
+
+int nbh_zone_collapse_f32(const float* values, const float* weights, float* out, int64_t n_lead, int32_t n_zones,
+                          int64_t n_points, void* stream) {
+  return nbh::run_zone_collapse(values, weights, out, n_lead, n_zones, n_points, static_cast<cudaStream_t>(stream));
 }
 
 int nbh_slice_stats_f32(const NbhDesc* desc, const float* in, NbhSliceStats* stats, void* stream) {

@@ -25,7 +25,6 @@
 #include "nbh_common.cuh"
 
 namespace nbh {
-int env_int(const char* name, int dflt);
 namespace {
 
 constexpr int kRfThreads = 128;
@@ -172,6 +171,7 @@ struct RfFuse {
   const float* cyp;          // y coefficients (tiled), nullptr = no fusion
   const uint8_t* zy;         // per-slice zero flags or nullptr
   unsigned* progress;        // [slice][tile row] tiles finished by the y-forward part
+  unsigned* ticket;          // fused sweeps: units are claimed in ticket order (forward progress, see below)
   long long n_slices;
 };
 
@@ -189,7 +189,16 @@ rf_x_kernel(float* __restrict__ g, const float* __restrict__ src, const float* _
   float* sc = sc_all[warp];
   long long* off0 = off_all[warp][0];                      // TILED: source rows; else data rows
   long long* off1 = off_all[warp][TILED ? 0 : 1];          // row-major coefficient rows
-  const long long unit = blockIdx.x * (long long)kRfXWarps + warp;
+  // Fused sweeps: a warp waits for the warp that owns the tile row above (unit - n_slices).  Units
+  // are therefore CLAIMED from an atomic ticket counter instead of being derived from blockIdx: the
+  // unit a warp depends on has a lower ticket, i.e. it was claimed by a warp that is already
+  // running, so the wait below always ends whatever order the blocks are scheduled in.
+  long long unit = blockIdx.x * (long long)kRfXWarps + warp;
+  if (TILED && fuse.cyp != nullptr) {
+    unsigned tk = 0;
+    if (lane == 0) tk = atomicAdd(fuse.ticket, 1u);
+    unit = (long long)__shfl_sync(0xffffffffu, tk, 0);
+  }
   if (unit >= n_units) return;
   int n_rows;
   long long gbase = 0, cbase = 0;      // TILED: first tile of this warp's tile row
@@ -342,11 +351,8 @@ rf_x_kernel(float* __restrict__ g, const float* __restrict__ src, const float* _
           if (lane == 0) {
             const volatile unsigned* p = fuse.progress + fs * TY + (fty - 1);
             const unsigned need = (unsigned)(nt - t);
-            // the producer was dispatched earlier and is at most a few tiles behind; a wait of
-            // seconds can only mean a scheduling assumption was violated: fail loudly, never hang
-            long long spins = 0;
-            while (*p < need)
-              if (++spins > (1LL << 23)) __trap();
+            // the producer holds a lower ticket: it is running and at most a few tiles behind
+            while (*p < need) __nanosleep(64);
           }
           __threadfence();
           __syncwarp();
@@ -511,8 +517,9 @@ int run_recursive_filter(const float* in, const float* cx, const float* cy, cons
   uint8_t* zy = per_slice ? zx + n_slices * plane : nullptr;
   uint8_t* after = per_slice ? zy + n_slices * plane : reinterpret_cast<uint8_t*>(cyp + plane);
   unsigned* progress = reinterpret_cast<unsigned*>((reinterpret_cast<uintptr_t>(after) + 255) & ~uintptr_t(255));
-  const bool fuse_on = env_int("NBH_RF_FUSE", 1) != 0;
-  RfFuse fuse{fuse_on ? cyp : nullptr, zy, progress, n_slices};
+  const bool fuse_on = true;      // y-forward sweep fused into the x-backward sweep (ticket-ordered wavefront)
+  unsigned* ticket = progress + n_slices * TY;
+  RfFuse fuse{fuse_on ? cyp : nullptr, zy, progress, ticket, n_slices};
   // a mask shared by all slices is folded into the coefficient planes; per-slice masks become flags
   dim3 cgrid((NX + 255) / 256, NY, 1);
   rf_pad_coeff_kernel<<<cgrid, 256, 0, st>>>(in, cx, cy, per_slice ? nullptr : mask, 0LL, 0, cxp, cyp, ny, nx, pad,
@@ -524,10 +531,10 @@ int run_recursive_filter(const float* in, const float* cx, const float* cy, cons
   }
   const long long n_units = n_slices * TY;
   const unsigned xb = (unsigned)((n_units + kRfXWarps - 1) / kRfXWarps);
-  const int ythreads = env_int("NBH_RF_YTHREADS", 128);
+  const int ythreads = 128;
   dim3 ygrid((NX + ythreads - 1) / ythreads, (unsigned)n_slices);
   for (int it = 0; it < iterations; ++it) {
-    if (fuse_on) NBH_CHECK_CUDA(cudaMemsetAsync(progress, 0, (size_t)n_slices * TY * 4, st));
+    if (fuse_on) NBH_CHECK_CUDA(cudaMemsetAsync(progress, 0, ((size_t)n_slices * TY + 1) * 4, st));
     // the first forward sweep builds the symmetric halo on the fly
     if (it == 0) {
       rf_x_kernel<true, true><<<xb, kRfXWarps * 32, 0, st>>>(g, in, cxp, n_units, 0, NY, NX, 0, 0, 0, 3, pad, ny, nx,

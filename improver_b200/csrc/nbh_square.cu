@@ -12,8 +12,6 @@
 // columns, no synchronisation), and (3) per output row does the horizontal
 // window sum as a difference of a float64 row prefix built with a warp-shuffle
 // scan, normalises by the valid-cell count and stores float32.
-#include "nbh_square_mt.cuh"
-#include "nbh_square_tma.cuh"
 #include "nbh_square_rs.cuh"
 #include "nbh_square_box.cuh"
 
@@ -227,11 +225,6 @@ static size_t sq_smem_bytes(int tx, int vec, int nb, bool masknd) {
   return b;
 }
 
-int env_int(const char* name, int dflt) {
-  const char* s = getenv(name);
-  return s && *s ? atoi(s) : dflt;
-}
-
 // Choose the strip width (threads per block), the y segmentation and the load
 // grouping.  Cost model: issue slots wasted on idle lanes, halo rows re-read
 // from HBM by every y segment, and the partially filled last wave.
@@ -240,19 +233,15 @@ static int plan_square(const NbhDesc& d, bool masknd, SqPlan* pl) {
   int vec = (d.nx % 4 == 0) ? 4 : (d.nx % 2 == 0 ? 2 : 1);
   if (r < 3) vec = min(vec, 2);          // edge-band flags need whole VEC groups inside r+1 columns
   if (r < 1) vec = 1;
-  vec = min(vec, env_int("NBH_SQ_VEC", 4));
   int dev = 0, smem_max = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (smem_max <= 0) smem_max = 227 * 1024;
-  const int forced_tx = env_int("NBH_SQ_TX", 0);
-  const int forced_ysegs = env_int("NBH_SQ_YSEGS", 0);
   const long long units = d.n_planes * (long long)max(d.n_thresholds, 1);
   double best_cost = 1e30;
   bool found = false;
   for (;;) {
     for (int tx = 64; tx <= kSqMaxThreads; tx += 32) {
-      if (forced_tx && tx != forced_tx) continue;
       const size_t smem = sq_smem_bytes(tx, vec, nb, masknd);
       if (smem > (size_t)smem_max) continue;
       const int WS = tx * vec;
@@ -267,7 +256,6 @@ static int plan_square(const NbhDesc& d, bool masknd, SqPlan* pl) {
       per_sm = max(per_sm, 1);
       const double slots = (double)sm_count() * per_sm;
       for (int ysegs = 1; ysegs <= 64; ++ysegs) {
-        if (forced_ysegs && ysegs != forced_ysegs) continue;
         const int seg_rows = (d.ny + ysegs - 1) / ysegs;
         if (ysegs > 1 && seg_rows < 4 * r) break;
         const int n_ysegs = (d.ny + seg_rows - 1) / seg_rows;
@@ -308,9 +296,7 @@ static bool plan_square_warp(const NbhDesc& d, int vec, SqWarpGeom* g) {
   // (two groups per lane waste fewer lanes but need > 128 registers, which costs
   // more in occupancy than it gains on B200: opt-in only)
   double best = 0.0;
-  const int forced = env_int("NBH_SQW_GROUPS", 1);
-  for (int groups = 1; groups <= (vec < 4 ? 2 : 1); ++groups) {
-    if (groups != forced && !(forced > 2)) continue;
+  for (int groups = 1; groups <= 1; ++groups) {
     const int WS = 32 * vec * groups;
     const int hl = (r + vec - 1) / vec * vec;
     const int W = (WS - hl - r) / vec * vec;
@@ -326,13 +312,13 @@ static bool plan_square_warp(const NbhDesc& d, int vec, SqWarpGeom* g) {
   }
   if (best == 0.0) return false;
   const long long units = d.n_planes * (long long)max(d.n_thresholds, 1) * g->n_strips;
-  int ysegs = env_int("NBH_SQW_YSEGS", 0);
-  if (ysegs <= 0) {
+  int ysegs = 0;
+  {
     // Warps are scheduled dynamically as blocks retire, so many small tasks
     // balance better than few large ones; every y segment re-reads 2r halo rows
     // (mostly L2 hits thanks to the alternating march direction).  Measured on
     // B200 (profiles/): ~5 tasks per resident warp slot is the sweet spot.
-    const double slots = (double)sm_count() * env_int("NBH_SQW_WPS", 16);
+    const double slots = (double)sm_count() * 16;
     const int max_segs = max(1, d.ny / max(32, 6 * r));
     ysegs = (int)min((double)max_segs, max(1.0, ceil(5.0 * slots / (double)units)));
   }
@@ -340,22 +326,17 @@ static bool plan_square_warp(const NbhDesc& d, int vec, SqWarpGeom* g) {
   g->seg_rows = (d.ny + ysegs - 1) / ysegs;
   g->n_ysegs = (d.ny + g->seg_rows - 1) / g->seg_rows;
   g->n_tasks = units * g->n_ysegs;
-  g->n_sm = env_int("NBH_SQW_REMAP", 0) ? sm_count() : 0;
+  g->n_sm = 0;
   return true;
 }
 
 bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid);
-
-bool make_square_tensor_map(const float* in, int ny, int nx, long long n_planes, int n_members,
-                            long long plane_stride, long long member_stride, int box_cols, CUtensorMap* map,
-                            int* super_rows);
 
 struct SqWorkspace {
   unsigned* edge_flags;
   SliceStats* stats;
   int* suspects;
   int* n_suspects;
-  CUtensorMap* tmap;
   double* rcp_count;
   float* cnt_plane;
   uint16_t* tmp;
@@ -371,7 +352,6 @@ static void carve_workspace(const NbhDesc& d, void* ws, SqWorkspace* w) {
   w->stats = reinterpret_cast<SliceStats*>(base + off); off = align_up(off + nslices * sizeof(SliceStats), 256);
   w->suspects = reinterpret_cast<int*>(base + off); off = align_up(off + nslices * 4, 256);
   w->n_suspects = reinterpret_cast<int*>(base + off); off = align_up(off + 4, 256);
-  w->tmap = reinterpret_cast<CUtensorMap*>(base + off); off = align_up(off + sizeof(CUtensorMap), 256);
   w->rcp_count = reinterpret_cast<double*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 8, 256);
   w->tmp = reinterpret_cast<uint16_t*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 2, 256);
   w->cnt_plane = reinterpret_cast<float*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 4, 256);
@@ -482,76 +462,41 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
   NBH_REQUIRE(blocks < (1LL << 31), "too many blocks (%lld); split the launch", blocks);
   int rc;
   SqWarpGeom wg;
-  const bool use_warp = !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && plan_square_warp(*d, pl.vec, &wg);
+  const bool use_warp = !masknd && plan_square_warp(*d, pl.vec, &wg);
   // fuzzy launches: pick the cheapest membership form every threshold of the launch supports
   int tm_warp = tm;
-  if (tm == 2 && !masknd && env_int("NBH_SQ_FASTKIND", 1)) {
+  if (tm == 2 && !masknd) {
     int kind = 5;
     for (int i = 0; i < d->n_thresholds; ++i) kind = min(kind, p.thr.t[i].fast_kind == 2 ? 2 : p.thr.t[i].fast_kind);
     tm_warp = kind;
   }
-  // TMA-fed variant: fused member path on grids whose rows (or row pairs) are 16-byte multiples
-  bool use_tma = false;
-  CUtensorMap tmap;
-  SqTmaGeom tg;
-  if (use_warp && pl.vec >= 2 && d->n_members >= 2 && d->n_members <= 32 && !(d->flags & NBH_WRAP_X) &&
-      env_int("NBH_SQ_TMA", 0)) {   // opt-in: measured 0.61 ms vs 0.57 ms for the register-pipelined kernel
-    SqWarpGeom wg2;
-    if (plan_square_warp(*d, 2, &wg2) && wg2.WS == 64 && d->nx >= kTmaWarps * wg2.W) {
-      // block tiles: kTmaWarps windows per block; the first block strip has no left halo
-      const int Wb = kTmaWarps * wg2.W, W0b = Wb + wg2.hl;
-      const int n_bstrips = 1 + (d->nx > W0b ? (d->nx - W0b + Wb - 1) / Wb : 0);
-      int super = 0;
-      const int box_cols = sq_tma_box_cols(wg2.WS, wg2.W);
-      if (box_cols <= 256 &&
-          make_square_tensor_map(in, d->ny, d->nx, d->n_planes, d->n_members, d->plane_stride, d->member_stride,
-                                 box_cols, &tmap, &super)) {
-        tg.super_rows = super;
-        tg.box_cols = box_cols;
-        tg.stage_floats = sq_tma_stage_floats(box_cols, d->n_members);
-        const int stages = env_int("NBH_SQ_TMA_STAGES", 3);
-        const size_t smem = sq_tma_smem_bytes(wg2.WS, wg2.W, p.nb, d->n_members, stages);
-        if (stages >= 2 && stages <= 8 && smem <= 200 * 1024) {
-          tg.n_stages = stages;
-          wg = wg2;
-          wg.n_strips = n_bstrips;
-          // re-plan the y segmentation for block tasks (3 blocks per SM)
-          const long long units = d->n_planes * (long long)max(d->n_thresholds, 1) * n_bstrips;
-          int ysegs = env_int("NBH_SQW_YSEGS", 0);
-          if (ysegs <= 0) {
-            const double slots = (double)sm_count() * 3;
-            const int max_segs = max(1, d->ny / max(32, 6 * d->cells));
-            ysegs = (int)min((double)max_segs, max(1.0, ceil(5.0 * slots / (double)units)));
-          }
-          ysegs = max(1, min(ysegs, d->ny));
-          wg.seg_rows = (d->ny + ysegs - 1) / ysegs;
-          wg.n_ysegs = (d->ny + wg.seg_rows - 1) / wg.seg_rows;
-          wg.n_tasks = units * wg.n_ysegs;
-          use_tma = true;
-        }
-      }
-    }
-  }
-  // several thresholds on the fused member path: read the input once per group of thresholds
-  SqWarpGeom wgm;
-  const bool use_mt = !use_tma && use_warp && pl.vec >= 2 && d->n_members >= 2 && d->n_thresholds >= 2 &&
-                      tm >= 1 && !(d->flags & NBH_WRAP_X) && env_int("NBH_SQ_MT", 0) &&   // opt-in: see profiles/r1_multi_threshold.jsonl
-                      plan_square_warp(*d, 2, &wgm) && wgm.WS == 64;
-  // single-member slices: the fixed-point box kernel (radius <= 8 cells), its guarded follow-ups,
-  // and for raw data the guarded float64 re-run of slices that are not probabilities
+  // Kernel choice (no run-time knobs):
+  //   members (fused threshold -> box sum -> realization mean): square_rs_kernel, else the warp kernel;
+  //   single-member slices, radius <= 8: square_box_kernel (+ guarded clamp / float64 re-run);
+  //   everything else (periodic x, odd widths, radius > 8): warp kernel; masked arrays and radii
+  //   beyond a warp strip: block-cooperative kernel.
   SqBoxGeom bg;
   int box_grid = 0;
   size_t box_smem = 0;
-  const bool use_box = !masknd && !use_tma && !use_mt && env_int("NBH_SQ_BOX", 1) &&
-                       plan_square_box(*d, in, &bg, &box_grid, &box_smem);
-  SqTileGeom tlg;
-  long long tile_blocks = 0;
-  size_t tile_smem = 0;
-  const bool use_tile = !use_box && !masknd && env_int("NBH_SQ_BLOCK", 0) == 0 && !use_tma && !use_mt &&
-                        !(d->flags & NBH_EXACT_SUMS) && plan_square_tile(*d, in, &tlg, &tile_blocks, &tile_smem);
+  const bool use_box = !masknd && plan_square_box(*d, in, &bg, &box_grid, &box_smem);
   SqRsGeom rg;
   int rs_grid = 0;
-  const bool use_rs = !use_box && !use_tile && use_warp && !use_tma && !use_mt && plan_square_rs(*d, in, &rg, &rs_grid);
+  const bool use_rs = !use_box && use_warp && plan_square_rs(*d, in, &rg, &rs_grid);
+  const bool m2d = d->mask2d != nullptr;
+  auto launch_exact = [&](const SqParams& pp) -> int {
+    if (use_warp) {
+      switch (pl.vec) {
+        case 4: return launch_square_warp_vec<4>(pp, wg, tm_warp, m2d, st);
+        case 2: return launch_square_warp_vec<2>(pp, wg, tm_warp, m2d, st);
+        default: return launch_square_warp_vec<1>(pp, wg, tm_warp, m2d, st);
+      }
+    }
+    switch (pl.vec) {
+      case 4: return launch_square_vec<4>(pp, pl, blocks, tm, masknd, m2d, st);
+      case 2: return launch_square_vec<2>(pp, pl, blocks, tm, masknd, m2d, st);
+      default: return launch_square_vec<1>(pp, pl, blocks, tm, masknd, m2d, st);
+    }
+  };
   if (use_box) {
     BoxWorkspace bw;
     box_carve(w.box, nslices, d->ny, d->nx, &bw);
@@ -559,79 +504,23 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
     bg.stats = bw.stats; bg.maskf = bw.maskf;
     {
       ProfileScope prof(st, "nbh::square_box_kernel (row-streaming, fixed-point, shuffle windows)");
-      rc = launch_square_box(p, bg, tm_warp, d->mask2d != nullptr, box_grid, box_smem, st);
+      rc = launch_square_box(p, bg, tm_warp, m2d, box_grid, box_smem, st);
     }
     if (rc) return rc;
     if (box_finish(bw, p, d->ext_stats, tm, nslices, st)) return 1;
     if (tm == 0) {
+      // raw slices that are not probabilities in [0, 1]: recomputed in float64 (guarded per slice)
       SqParams pr = p;
       pr.redo = bw.redo;
-      const bool m2d = d->mask2d != nullptr;
-      if (use_warp) {
-        switch (pl.vec) {
-          case 4: rc = launch_square_warp_vec<4>(pr, wg, tm_warp, m2d, st); break;
-          case 2: rc = launch_square_warp_vec<2>(pr, wg, tm_warp, m2d, st); break;
-          default: rc = launch_square_warp_vec<1>(pr, wg, tm_warp, m2d, st); break;
-        }
-      } else {
-        switch (pl.vec) {
-          case 4: rc = launch_square_vec<4>(pr, pl, blocks, tm, masknd, m2d, st); break;
-          case 2: rc = launch_square_vec<2>(pr, pl, blocks, tm, masknd, m2d, st); break;
-          default: rc = launch_square_vec<1>(pr, pl, blocks, tm, masknd, m2d, st); break;
-        }
-      }
+      rc = launch_exact(pr);
     }
-  } else
-  if (use_tile) {
-    ProfileScope prof(st, "nbh::square_tile_kernel (separable running sums in independent tiles)");
-    rc = launch_square_tile(p, tlg, tm_warp, d->mask2d != nullptr, tile_blocks, tile_smem, st);
   } else if (use_rs) {
     ProfileScope prof(st, "nbh::square_rs_kernel (row-streaming, bulk-copy staged rows)");
-    rc = launch_square_rs(p, rg, tm_warp, d->mask2d != nullptr, rs_grid, st);
-  } else if (use_mt) {
-    // tasks do not include the threshold index: re-plan the y segmentation for 12 warps / SM
-    const long long units = d->n_planes * (long long)wgm.n_strips;
-    int ysegs = env_int("NBH_SQW_YSEGS", 0);
-    if (ysegs <= 0) {
-      const double slots = (double)sm_count() * 12;
-      const int max_segs = max(1, d->ny / max(32, 6 * d->cells));
-      ysegs = (int)min((double)max_segs, max(1.0, ceil(5.0 * slots / (double)units)));
-    }
-    ysegs = max(1, min(ysegs, d->ny));
-    wgm.seg_rows = (d->ny + ysegs - 1) / ysegs;
-    wgm.n_ysegs = (d->ny + wgm.seg_rows - 1) / wgm.seg_rows;
-    wgm.n_tasks = units * wgm.n_ysegs;
-    wgm.n_sm = 0;
-    ProfileScope prof(st, "nbh::square_mt_kernel");
-    rc = 0;
-    for (int t0 = 0; t0 < d->n_thresholds && rc == 0; t0 += kMtThresholds) {
-      SqParams pg = p;
-      SqMtParams mt;
-      mt.t_base = t0;
-      mt.n_launch = min(kMtThresholds, d->n_thresholds - t0);
-      for (int i = 0; i < mt.n_launch; ++i) pg.thr.t[i] = p.thr.t[t0 + i];
-      rc = launch_square_mt(pg, wgm, mt, tm_warp, d->mask2d != nullptr, st);
-    }
-  } else if (use_tma) {
-    NBH_CHECK_CUDA(cudaMemcpyAsync(w.tmap, &tmap, sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
-    ProfileScope prof(st, "nbh::square_tma_kernel");
-    rc = launch_square_tma(p, wg, tg, w.tmap, tm_warp, d->mask2d != nullptr, st);
-  } else if (use_warp) {
-    ProfileScope prof(st, "nbh::square_warp_kernel (warp-autonomous strips)");
-    const bool m2d = d->mask2d != nullptr;
-    switch (pl.vec) {
-      case 4: rc = launch_square_warp_vec<4>(p, wg, tm_warp, m2d, st); break;
-      case 2: rc = launch_square_warp_vec<2>(p, wg, tm_warp, m2d, st); break;
-      default: rc = launch_square_warp_vec<1>(p, wg, tm_warp, m2d, st); break;
-    }
+    rc = launch_square_rs(p, rg, tm_warp, m2d, rs_grid, st);
   } else {
-    ProfileScope prof(st, "nbh::square_kernel (block-cooperative strips)");
-    const bool m2d = d->mask2d != nullptr;
-    switch (pl.vec) {
-      case 4: rc = launch_square_vec<4>(p, pl, blocks, tm, masknd, m2d, st); break;
-      case 2: rc = launch_square_vec<2>(p, pl, blocks, tm, masknd, m2d, st); break;
-      default: rc = launch_square_vec<1>(p, pl, blocks, tm, masknd, m2d, st); break;
-    }
+    ProfileScope prof(st, use_warp ? "nbh::square_warp_kernel (warp-autonomous strips)"
+                                   : "nbh::square_kernel (block-cooperative strips)");
+    rc = launch_exact(p);
   }
   if (rc) return rc;
   if (!sum_only) {

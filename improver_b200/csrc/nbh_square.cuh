@@ -40,17 +40,6 @@ struct SqPlan {
   size_t smem;
 };
 
-// tile kernel for single-member slices (nbh_square_tile.cu)
-struct SqTileGeom {
-  int tiles_x, tiles_y;
-  int sw;                // staged row pitch (floats)
-  int n_cnt;             // entries of the reciprocal table: (2r+1)^2
-  int vec2;              // rows are 8-byte aligned: interior tiles load and stage float2
-};
-bool plan_square_tile(const NbhDesc& d, const float* in, SqTileGeom* g, long long* blocks, size_t* smem);
-int launch_square_tile(const SqParams& p, const SqTileGeom& g, int tm, bool m2d, long long blocks, size_t smem,
-                       cudaStream_t st);
-
 // how the (row, member) loads of a block are grouped into register chunks
 enum { SQ_ROWS = 0,          // n_members == 1: a chunk is MB consecutive rows
        SQ_MEMBERS_FULL = 1,  // n_members == MB: a chunk is one row of all members

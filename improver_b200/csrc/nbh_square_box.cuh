@@ -30,6 +30,8 @@
 // float64 kernels, slices whose results left [min, max] by the quantisation are clamped
 // (nbhood.py:312).
 #pragma once
+#include <type_traits>
+
 #include "nbh_square_rs.cuh"
 
 namespace nbh {
@@ -42,7 +44,10 @@ constexpr int kBoxK = 8;                     // columns per lane
 constexpr int kBoxWinCols = 32 * kBoxK;      // 256
 constexpr int kBoxUseful = 30 * kBoxK;       // 240: lanes 1..30 produce outputs
 constexpr int kBoxMaxStages = 8;
-constexpr int kBoxBPlain = 4, kBoxBMasked = 2;   // rows per stage / batch (masked launches stage a mask row per data row)
+#ifndef NBH_BOX_BPLAIN
+#define NBH_BOX_BPLAIN 2
+#endif
+constexpr int kBoxBPlain = NBH_BOX_BPLAIN, kBoxBMasked = 2;   // rows per stage / batch (masked launches stage a mask row per data row)
 
 // per-slice extremes recorded by the box kernel (ordered-int keys, see float_key)
 struct BoxStats {
@@ -84,6 +89,15 @@ __device__ __forceinline__ float max3f(float a, float b, float c) { return fmaxf
 __device__ __forceinline__ void lds_f4(unsigned addr, float* v) {
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(addr));
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+8];" : "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+
+// barrier wait: plain try_wait loop (the hardware blocks the thread for a short, bounded time per
+// try); a suspend-time hint turns every miss into a ~1 us sleep, which with a handful of stages
+// in flight serialises the producer / consumer hand-over (ncu r2c: half of the executed
+// instructions were SYNCS / NANOSLEEP / BRA of those loops, DRAM at 26 %)
+__device__ __forceinline__ void box_wait(unsigned bar, unsigned parity, unsigned hint_ns) {
+  if (hint_ns) mbar_wait_hint(bar, parity, hint_ns);
+  else mbar_wait(bar, parity);
 }
 
 template <int R, int TM, bool M2D>
@@ -137,7 +151,7 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
       for (int k = 0; k < n_in; k += B) {
         const int n = min(B, n_in - k);
         const int y0 = y_lo + k;
-        mbar_wait_hint(empty0 + 8 * s, (round & 1u) ^ 1u, g.wait_ns);
+        box_wait(empty0 + 8 * s, (round & 1u) ^ 1u, g.wait_ns);
         const unsigned dst0 = stage0 + (unsigned)s * stage_bytes;
         if (g.contiguous) {
           // one copy of n full rows (+ one for the mask rows); the producers take the stages in turn
@@ -199,10 +213,12 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
   unsigned* ring = reinterpret_cast<unsigned*>(bars + 2 * kBoxMaxStages) + (size_t)warp * NB * kBoxWinCols;
   const unsigned ring_u32 = smem_u32(ring) + (unsigned)lane * (K * 4u);
   const bool sum_only = (p.flags & NBH_SUM_ONLY) != 0;
+  const bool want_stats = !sum_only || TM == 0;
   const float fx_scale = (float)(1u << g.fx_shift);
   const unsigned ONE = 1u << g.fx_shift;
   const float fx_inv = 1.0f / fx_scale;
   const unsigned stages_u32 = smem_u32(stages);
+  const float kInf = __int_as_float(0x7f800000);
   float nanacc = 0.f;
   int s = 0;
   unsigned parity = 0, bar = full0, st_addr = stages_u32;
@@ -220,15 +236,16 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
     const int seg0 = max(gw0 * kBoxUseful - K, 0);          // first staged column of the panel
     const int x0 = gw * kBoxUseful - K + lane * K;          // first column of this lane
     const bool win_active = gw < NBP;
-    // columns of this lane inside the domain; a lane that is not fully inside reads the nearest
-    // fully valid group instead (its values are then zeroed / excluded explicitly)
+    // Columns of this lane inside the domain.  Every lane reads the eight values at its own
+    // columns (a lane without any valid column reads the first staged group instead); what lies
+    // beyond the end of a row is other staged data, it is masked out of the sums (colmask) and
+    // kept out of the statistics (partial lanes take the predicated path).
     unsigned okbits = 0;
 #pragma unroll
     for (int i = 0; i < K; ++i) okbits |= (win_active && x0 + i >= 0 && x0 + i < p.nx) ? (1u << i) : 0u;
     const bool lane_full = okbits == 0xffu;
     const bool warp_edge = __any_sync(0xffffffffu, !lane_full);
-    const int x_ld = lane_full ? x0 : (x0 < 0 || !win_active ? seg0 : max(seg0, ((p.nx - K) & ~1)));
-    const int ld_shift = lane_full ? 0 : (x0 >= 0 && win_active ? x0 - x_ld : 0);   // partial lane: columns moved right by this
+    const int x_ld = okbits ? x0 : seg0;
     const bool out_lane = lane >= 1 && lane <= 30 && okbits != 0;
     const bool band_l = !sum_only && okbits && x0 <= R;
     const bool band_r = !sum_only && okbits && x0 + K - 1 >= p.nx - 1 - R;
@@ -240,15 +257,7 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
     const long long obase0 = unit * (long long)p.ny * p.nx;
     const unsigned long long plane_elem0 = in_elem0 + (unsigned long long)(plane * p.plane_stride) + (unsigned long long)seg0;
     const unsigned lane_col_b = (unsigned)(x_ld - seg0) * 4u;
-
-    // normalisation constants: interior lanes share the row's reciprocal, edge lanes keep per-column counts
-    float ncol[K];
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-      const int xo = x0 + i;
-      ncol[i] = (float)(min(xo + R, p.nx - 1) - max(xo - R, 0) + 1);
-    }
-    const bool lane_interior = (x0 - R >= 0) && (x0 + K - 1 + R <= p.nx - 1);
+    const bool lane_interior = lane_full && (x0 - R >= 0) && (x0 + K - 1 + R <= p.nx - 1);
 
     // zero the ring (rows above the domain are zeros)
 #pragma unroll
@@ -260,8 +269,7 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
 #pragma unroll
     for (int i = 0; i < K; ++i) V[i] = 0u;
     int slot = 0;
-    float dmin = __int_as_float(0x7f800000), dmax = __int_as_float(0xff800000);
-    float omin = __int_as_float(0x7f800000), omax = __int_as_float(0xff800000);
+    float dmin = kInf, dmax = -kInf, omin = kInf, omax = -kInf;
     unsigned ne_bits = 0;                                   // bit0 top, bit1 bottom, bit2 left, bit3 right
     __syncwarp();
 
@@ -276,29 +284,26 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
       float mk[M2D ? B : 1][K];
       if (has_data) {
         nbr = min(B, n_in_piece - consumed);
-        mbar_wait_hint(bar, parity, g.wait_ns);
+        box_wait(bar, parity, g.wait_ns);
         const unsigned long long e0 = plane_elem0 + (unsigned long long)((long long)yy0 * p.nx);
         const unsigned long long m0 = M2D ? mk_elem0 + (unsigned long long)((long long)yy0 * p.nx + seg0) : 0ull;
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-          if (j < nbr) {
-            unsigned off, moff = 0;
-            if (g.contiguous) {
-              off = (unsigned)(e0 & 3ull) * 4u + (unsigned)(j * p.nx) * 4u;
-              if (M2D) moff = (unsigned)(m0 & 3ull) * 4u + (unsigned)(j * p.nx) * 4u;
-            } else {
-              off = (unsigned)((e0 + (unsigned long long)(j * p.nx)) & 3ull) * 4u + (unsigned)(j * g.seg_pitch) * 4u;
-              if (M2D) moff = (unsigned)((m0 + (unsigned long long)(j * p.nx)) & 3ull) * 4u + (unsigned)(j * g.seg_pitch) * 4u;
-            }
-            lds_f4(st_addr + off + lane_col_b, &d[j][0]);
-            lds_f4(st_addr + off + lane_col_b + 16u, &d[j][4]);
-            if (M2D) {
-              lds_f4(st_addr + (unsigned)g.mask_off * 4u + moff + lane_col_b, &mk[j][0]);
-              lds_f4(st_addr + (unsigned)g.mask_off * 4u + moff + lane_col_b + 16u, &mk[j][4]);
-            }
+          // rows past the end of the piece re-read the first row of the stage (ignored later)
+          const int jj = j < nbr ? j : 0;
+          unsigned off, moff = 0;
+          if (g.contiguous) {
+            off = (unsigned)(e0 & 3ull) * 4u + (unsigned)(jj * p.nx) * 4u;
+            if (M2D) moff = (unsigned)(m0 & 3ull) * 4u + (unsigned)(jj * p.nx) * 4u;
           } else {
-#pragma unroll
-            for (int i = 0; i < K; ++i) { d[j][i] = 0.f; if (M2D) mk[j][i] = 0.f; }
+            off = (unsigned)((e0 + (unsigned long long)(jj * p.nx)) & 3ull) * 4u + (unsigned)(jj * g.seg_pitch) * 4u;
+            if (M2D) moff = (unsigned)((m0 + (unsigned long long)(jj * p.nx)) & 3ull) * 4u + (unsigned)(jj * g.seg_pitch) * 4u;
+          }
+          lds_f4(st_addr + off + lane_col_b, &d[j][0]);
+          lds_f4(st_addr + off + lane_col_b + 16u, &d[j][4]);
+          if (M2D) {
+            lds_f4(st_addr + (unsigned)g.mask_off * 4u + moff + lane_col_b, &mk[j][0]);
+            lds_f4(st_addr + (unsigned)g.mask_off * 4u + moff + lane_col_b + 16u, &mk[j][4]);
           }
         }
         consumed += nbr;
@@ -314,100 +319,151 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
           for (int i = 0; i < K; ++i) { d[j][i] = 0.f; if (M2D) mk[j][i] = 0.f; }
       }
 
-      // ---- quantise, vertical running sums (sequential over the rows of the batch) ----
-      unsigned Vs[B][K];
+      // The batch body, specialised on FULL (every row of the batch is a data row that completes
+      // an output row: no per-row conditions, so the independent rows interleave) and written as
+      // one loop over the rows per step of the computation.
+      auto batch = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        // ---- 1. extremes of the raw data; NaN propagates through the maximum (nbhood.py:167-168) ----
+        if (has_data) {
+          if (lane_full) {
 #pragma unroll
-      for (int j = 0; j < B; ++j) {
-        if (j < nbr) {
-          unsigned q[K];
-          if (has_data) {
-            if (!sum_only || TM == 0) {
-              // extremes of the raw data (NaN propagates through the maximum: nbhood.py:167-168)
-              dmax = max3_nan(dmax, d[j][0], d[j][1]); dmax = max3_nan(dmax, d[j][2], d[j][3]);
-              dmax = max3_nan(dmax, d[j][4], d[j][5]); dmax = max3_nan(dmax, d[j][6], d[j][7]);
-              dmin = min3f(dmin, d[j][0], d[j][1]); dmin = min3f(dmin, d[j][2], d[j][3]);
-              dmin = min3f(dmin, d[j][4], d[j][5]); dmin = min3f(dmin, d[j][6], d[j][7]);
-            } else {
-              nanacc = max3_nan(nanacc, d[j][0], d[j][1]); nanacc = max3_nan(nanacc, d[j][2], d[j][3]);
-              nanacc = max3_nan(nanacc, d[j][4], d[j][5]); nanacc = max3_nan(nanacc, d[j][6], d[j][7]);
-            }
-#pragma unroll
-            for (int i = 0; i < K; ++i) {
-              float tv = truth_value_sum<TM>(d[j][i], thr);
-              if (M2D) tv *= mk[j][i];
-              q[i] = __float2uint_rn(tv * fx_scale);
-            }
-            if (warp_edge && !lane_full) {
-              // a lane straddling the right edge loaded the last eight columns of the row instead:
-              // its column i sits at position i + ld_shift (2, 4 or 6) of the loaded group
-              if (okbits == 0u) {
-#pragma unroll
-                for (int i = 0; i < K; ++i) q[i] = 0u;
-              } else if (ld_shift == 2) {
-                q[0] = q[2]; q[1] = q[3]; q[2] = q[4]; q[3] = q[5]; q[4] = q[6]; q[5] = q[7]; q[6] = 0u; q[7] = 0u;
-              } else if (ld_shift == 4) {
-                q[0] = q[4]; q[1] = q[5]; q[2] = q[6]; q[3] = q[7]; q[4] = 0u; q[5] = 0u; q[6] = 0u; q[7] = 0u;
-              } else {
-                q[0] = q[6]; q[1] = q[7]; q[2] = 0u; q[3] = 0u; q[4] = 0u; q[5] = 0u; q[6] = 0u; q[7] = 0u;
+            for (int j = 0; j < B; ++j) {
+              if (FULL || j < nbr) {
+                const float a = max3_nan(d[j][0], d[j][1], d[j][2]), b2 = max3_nan(d[j][3], d[j][4], d[j][5]);
+                const float c = max3_nan(d[j][6], d[j][7], a);
+                if (want_stats) {
+                  dmax = max3_nan(dmax, b2, c);
+                  const float e = min3f(d[j][0], d[j][1], d[j][2]), f = min3f(d[j][3], d[j][4], d[j][5]);
+                  dmin = min3f(dmin, min3f(d[j][6], d[j][7], e), f);
+                } else {
+                  nanacc = max3_nan(nanacc, b2, c);
+                }
               }
             }
+          } else if (okbits) {
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+              if (FULL || j < nbr) {
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                  if ((okbits >> i) & 1u) {
+                    if (want_stats) { dmax = max_nan(dmax, d[j][i]); dmin = fminf(dmin, d[j][i]); }
+                    else nanacc = max_nan(nanacc, d[j][i]);
+                  }
+                }
+              }
+            }
+          }
+        }
+        // ---- 2. truth values -> fixed point ----
+        unsigned q[B][K];
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+#pragma unroll
+          for (int i = 0; i < K; ++i) {
+            float tv = truth_value_sum<TM>(d[j][i], thr);
+            if (M2D) tv *= mk[j][i];
+            q[j][i] = __float2uint_rn(tv * fx_scale);
+          }
+        }
+        if (warp_edge || !has_data) {
+#pragma unroll
+          for (int j = 0; j < B; ++j)
+#pragma unroll
+            for (int i = 0; i < K; ++i) q[j][i] = (has_data && ((okbits >> i) & 1u)) ? q[j][i] : 0u;
+        }
+        // ---- 3. edge bands of the trimming fix-up: has a value != 1 been seen? (sticky) ----
+        if (!sum_only && has_data) {
+          const bool cols_open = (band_l && !(ne_bits & 4u)) || (band_r && !(ne_bits & 8u));
+#pragma unroll
+          for (int j = 0; j < B; ++j) {
             const int yy = yy0 + j;
-            if (!sum_only && (yy <= R || yy >= p.ny - 1 - R || band_l || band_r)) {
-              unsigned ne = 0;
+            const bool rows_band = yy <= R || yy >= p.ny - 1 - R;
+            if ((FULL || j < nbr) && (rows_band || cols_open)) {
 #pragma unroll
               for (int i = 0; i < K; ++i) {
                 const int xo = x0 + i;
-                const bool okc = (okbits >> i) & 1u;
-                const bool n1 = okc && q[i] != ONE;
-                if (n1) {
-                  if (yy <= R) ne |= 1u;
-                  if (yy >= p.ny - 1 - R) ne |= 2u;
-                  if (xo <= R) ne |= 4u;
-                  if (xo >= p.nx - 1 - R) ne |= 8u;
+                if (((okbits >> i) & 1u) && q[j][i] != ONE) {
+                  if (yy <= R) ne_bits |= 1u;
+                  if (yy >= p.ny - 1 - R) ne_bits |= 2u;
+                  if (xo <= R) ne_bits |= 4u;
+                  if (xo >= p.nx - 1 - R) ne_bits |= 8u;
                 }
               }
-              ne_bits |= ne;
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < K; ++i) q[i] = 0u;
           }
-          // ring exchange: V += q - ring[slot]; ring[slot] = q
-          const unsigned ra = ring_u32 + (unsigned)slot * (kBoxWinCols * 4u);
-          unsigned o[K];
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(ra));
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]) : "r"(ra));
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]) : "memory");
-          asm volatile("st.shared.v4.u32 [%0+16], {%1, %2, %3, %4};" ::"r"(ra), "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7]) : "memory");
-#pragma unroll
-          for (int i = 0; i < K; ++i) { V[i] += q[i] - o[i]; Vs[j][i] = V[i]; }
-          slot = (slot + 1 == NB) ? 0 : slot + 1;
-        } else {
-#pragma unroll
-          for (int i = 0; i < K; ++i) Vs[j][i] = 0u;
         }
-      }
-
-      // ---- horizontal windows from the neighbours' column sums, normalise, store ----
+        // ---- 4. ring exchange and vertical running sums (sequential over the rows) ----
+        unsigned Vs[B][K];
+        if (NB >= B) {
+          // the B rows of the batch occupy distinct ring slots: all loads first, then the stores
+          unsigned o[B][K];
+          int sl[B];
 #pragma unroll
-      for (int j = 0; j < B; ++j) {
-        if (j < nbr && k + j >= 2 * R) {                    // warp-uniform
-          unsigned E[K + 2 * R];
+          for (int j = 0; j < B; ++j) { sl[j] = slot; slot = (slot + 1 == NB) ? 0 : slot + 1; }
 #pragma unroll
-          for (int i = 0; i < R; ++i) {
-            E[i] = __shfl_up_sync(0xffffffffu, Vs[j][K - R + i], 1);
-            E[K + R + i] = __shfl_down_sync(0xffffffffu, Vs[j][i], 1);
+          for (int j = 0; j < B; ++j) {
+            if (FULL || j < nbr) {
+              const unsigned ra = ring_u32 + (unsigned)sl[j] * (kBoxWinCols * 4u);
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o[j][0]), "=r"(o[j][1]), "=r"(o[j][2]), "=r"(o[j][3]) : "r"(ra));
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(o[j][4]), "=r"(o[j][5]), "=r"(o[j][6]), "=r"(o[j][7]) : "r"(ra));
+            }
           }
 #pragma unroll
-          for (int i = 0; i < K; ++i) E[R + i] = Vs[j][i];
-          unsigned H[K];
-          unsigned acc = E[0];
+          for (int j = 0; j < B; ++j) {
+            if (FULL || j < nbr) {
+              const unsigned ra = ring_u32 + (unsigned)sl[j] * (kBoxWinCols * 4u);
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(q[j][0]), "r"(q[j][1]), "r"(q[j][2]), "r"(q[j][3]) : "memory");
+              asm volatile("st.shared.v4.u32 [%0+16], {%1, %2, %3, %4};" ::"r"(ra), "r"(q[j][4]), "r"(q[j][5]), "r"(q[j][6]), "r"(q[j][7]) : "memory");
 #pragma unroll
-          for (int c = 1; c <= 2 * R; ++c) acc += E[c];
-          H[0] = acc;
+              for (int i = 0; i < K; ++i) { V[i] += q[j][i] - o[j][i]; Vs[j][i] = V[i]; }
+            } else {
 #pragma unroll
-          for (int i = 1; i < K; ++i) H[i] = H[i - 1] + E[i + 2 * R] - E[i - 1];
-          if (out_lane) {
+              for (int i = 0; i < K; ++i) Vs[j][i] = 0u;
+            }
+          }
+          if (!FULL) slot = (sl[0] + nbr) % NB;             // only nbr rows entered the ring
+        } else {
+          // a batch longer than the ring (radius 1 with four rows): strictly row by row
+#pragma unroll
+          for (int j = 0; j < B; ++j) {
+            if (FULL || j < nbr) {
+              const unsigned ra = ring_u32 + (unsigned)slot * (kBoxWinCols * 4u);
+              unsigned o[K];
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(ra) : "memory");
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]) : "r"(ra) : "memory");
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(q[j][0]), "r"(q[j][1]), "r"(q[j][2]), "r"(q[j][3]) : "memory");
+              asm volatile("st.shared.v4.u32 [%0+16], {%1, %2, %3, %4};" ::"r"(ra), "r"(q[j][4]), "r"(q[j][5]), "r"(q[j][6]), "r"(q[j][7]) : "memory");
+#pragma unroll
+              for (int i = 0; i < K; ++i) { V[i] += q[j][i] - o[i]; Vs[j][i] = V[i]; }
+              slot = (slot + 1 == NB) ? 0 : slot + 1;
+            } else {
+#pragma unroll
+              for (int i = 0; i < K; ++i) Vs[j][i] = 0u;
+            }
+          }
+        }
+        // ---- 5. horizontal windows from the neighbours' column sums; normalise; store ----
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+          if (FULL || (j < nbr && k + j >= 2 * R)) {          // warp-uniform
+            unsigned E[K + 2 * R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+              E[i] = __shfl_up_sync(0xffffffffu, Vs[j][K - R + i], 1);
+              E[K + R + i] = __shfl_down_sync(0xffffffffu, Vs[j][i], 1);
+            }
+#pragma unroll
+            for (int i = 0; i < K; ++i) E[R + i] = Vs[j][i];
+            // H[0] as a balanced sum, then H[i] = H[i-1] + entering - leaving
+            unsigned part[3] = {0u, 0u, 0u};
+#pragma unroll
+            for (int c = 0; c <= 2 * R; ++c) part[c % 3] += E[c];
+            unsigned H[K];
+            H[0] = part[0] + part[1] + part[2];
+#pragma unroll
+            for (int i = 1; i < K; ++i) H[i] = H[i - 1] + E[i + 2 * R] - E[i - 1];
             const int yo = y_first + k + j - R;
             const int rows_in = min(yo + R, p.ny - 1) - max(yo - R, 0) + 1;
             const long long pt0 = (long long)yo * p.nx + x0;
@@ -418,7 +474,7 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
             } else if (M2D) {
 #pragma unroll
               for (int i = 0; i < K; ++i) {
-                const float cnt = ((okbits >> i) & 1u) ? __ldg(p.cnt_plane + pt0 + i) : 1.f;
+                const float cnt = (out_lane && ((okbits >> i) & 1u)) ? __ldg(p.cnt_plane + pt0 + i) : 1.f;
                 const float nf = cnt * fx_scale;
                 float rc;
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(nf));
@@ -429,46 +485,56 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
               }
             } else {
               const float nrow = (float)rows_in * fx_scale;
+              const float nfi = nrow * (float)NB;
+              float rci;
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rci) : "f"(nfi));
 #pragma unroll
               for (int i = 0; i < K; ++i) {
-                const float nf = nrow * (lane_interior ? (float)NB : ncol[i]);
-                float rc;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(nf));
+                float nf = nfi, rc = rci;
+                if (!lane_interior) {
+                  const int xo = x0 + i;
+                  nf = nrow * (float)(min(xo + R, p.nx - 1) - max(xo - R, 0) + 1);
+                  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(nf));
+                }
                 const float Sf = (float)H[i];
                 const float q0 = Sf * rc;
                 const float rem = __fmaf_rn(-q0, nf, Sf);
                 o[i] = __fmaf_rn(rem, rc, q0);
               }
             }
-            if (lane_full) {
-              if (!sum_only) {
-                omax = max3f(omax, o[0], o[1]); omax = max3f(omax, o[2], o[3]);
-                omax = max3f(omax, o[4], o[5]); omax = max3f(omax, o[6], o[7]);
-                omin = min3f(omin, o[0], o[1]); omin = min3f(omin, o[2], o[3]);
-                omin = min3f(omin, o[4], o[5]); omin = min3f(omin, o[6], o[7]);
-              }
-              float* op = p.out + obase0 + pt0;
-              *reinterpret_cast<float2*>(op) = make_float2(o[0], o[1]);
-              *reinterpret_cast<float2*>(op + 2) = make_float2(o[2], o[3]);
-              *reinterpret_cast<float2*>(op + 4) = make_float2(o[4], o[5]);
-              *reinterpret_cast<float2*>(op + 6) = make_float2(o[6], o[7]);
-            } else {
+            if (out_lane) {
+              if (lane_full) {
+                if (!sum_only) {
+                  omax = max3f(omax, max3f(o[0], o[1], o[2]), max3f(o[3], o[4], o[5]));
+                  omax = max3f(omax, o[6], o[7]);
+                  omin = min3f(omin, min3f(o[0], o[1], o[2]), min3f(o[3], o[4], o[5]));
+                  omin = min3f(omin, o[6], o[7]);
+                }
+                float* op = p.out + obase0 + pt0;
+                *reinterpret_cast<float2*>(op) = make_float2(o[0], o[1]);
+                *reinterpret_cast<float2*>(op + 2) = make_float2(o[2], o[3]);
+                *reinterpret_cast<float2*>(op + 4) = make_float2(o[4], o[5]);
+                *reinterpret_cast<float2*>(op + 6) = make_float2(o[6], o[7]);
+              } else {
 #pragma unroll
-              for (int i = 0; i < K; ++i) {
-                if ((okbits >> i) & 1u) {
-                  if (!sum_only) { omax = fmaxf(omax, o[i]); omin = fminf(omin, o[i]); }
-                  p.out[obase0 + pt0 + i] = o[i];
+                for (int i = 0; i < K; ++i) {
+                  if ((okbits >> i) & 1u) {
+                    if (!sum_only) { omax = fmaxf(omax, o[i]); omin = fminf(omin, o[i]); }
+                    p.out[obase0 + pt0 + i] = o[i];
+                  }
                 }
               }
-            }
-            if (p.out_mask) {
+              if (p.out_mask) {
 #pragma unroll
-              for (int i = 0; i < K; ++i)
-                if ((okbits >> i) & 1u) p.out_mask[obase0 + pt0 + i] = (M2D && p.mask2d[pt0 + i] == 0) ? 1 : 0;
+                for (int i = 0; i < K; ++i)
+                  if ((okbits >> i) & 1u) p.out_mask[obase0 + pt0 + i] = (M2D && p.mask2d[pt0 + i] == 0) ? 1 : 0;
+              }
             }
           }
         }
-      }
+      };
+      if (has_data && nbr == B && k >= 2 * R) batch(std::true_type{});
+      else batch(std::false_type{});
       k += nbr;
     }
 
@@ -477,11 +543,12 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
       const unsigned bits = __reduce_or_sync(0xffffffffu, ne_bits);
       if (lane == 0 && bits) atomicOr(p.edge_flags + (plane * p.n_thr + t), bits);
     }
-    if (!sum_only || TM == 0) {
+    if (want_stats) {
       // NaN in dmax marks the launch; the keys of the finite extremes go to the slice record
       if (__isnanf(dmax)) nanacc = dmax;
-      int kmin = __isnanf(dmin) ? INT_MAX : box_float_key(dmin), kmax = __isnanf(dmax) ? INT_MIN : box_float_key(dmax);
-      int komin = box_float_key(omin), komax = box_float_key(omax);
+      int kmin = (__isnanf(dmin) || dmin == kInf) ? INT_MAX : box_float_key(dmin);
+      int kmax = (__isnanf(dmax) || dmax == -kInf) ? INT_MIN : box_float_key(dmax);
+      int komin = omin == kInf ? INT_MAX : box_float_key(omin), komax = omax == -kInf ? INT_MIN : box_float_key(omax);
       kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
       komin = __reduce_min_sync(0xffffffffu, komin); komax = __reduce_max_sync(0xffffffffu, komax);
       if (lane == 0) {

@@ -28,17 +28,16 @@
 // rows two neighbouring shares have in common are read at about the same time
 // (L2 hit).
 //
-// Two modes.  Members mode (n_members >= 2, the fused threshold -> box sum ->
-// realization mean): a stage holds `ms` member rows of one grid row.  Rows mode
-// (n_members == 1): consecutive rows of a slice are contiguous, a stage is ONE
-// copy of up to four rows, and the rows of a stage are processed as a batch so
-// that their scans interleave.
+// A stage holds `ms` member rows of one grid row (n_members >= 2: the fused
+// threshold -> box sum -> realization mean).  Single-member slices are the
+// business of square_box_kernel (nbh_square_box.cuh).
 //
 // Arithmetic: float32 member sum; thresholded launches then use exact unsigned
 // fixed-point vertical / horizontal window sums (see the consumer section),
 // raw-data launches the float64 sums of square_warp_kernel.
 #pragma once
-#include "nbh_square_tma.cuh"
+#include "nbh_async.cuh"
+#include "nbh_square_warp.cuh"
 
 namespace nbh {
 
@@ -48,7 +47,6 @@ constexpr int kRsProducers = 4;                         // producer warps: one t
                                                         // so the member rows of a stage are issued by four threads
 constexpr int kRsThreads = (kRsMaxWindows + kRsProducers) * 32;
 constexpr int kRsMaxStages = 16;
-constexpr int kRsBatch = 4;                             // rows-mode: rows of a stage processed together
 
 struct SqRsGeom {
   int n_windows;        // consumer warps = 64-column windows per x panel
@@ -56,8 +54,6 @@ struct SqRsGeom {
   int n_windows_total;  // windows per full row
   int W0, W, hl;        // output columns of window 0 / the others, left halo (even, >= r)
   int ms;               // items (member rows) per stage; divides n_members
-  int rps;              // > 0: single-member launches, a stage holds up to rps consecutive rows of the march
-                        // (one contiguous bulk copy; ms == 1 and pitch covers rps rows)
   int n_stages;
   int pitch;            // floats per staged item (multiple of 4)
   long long rows_total; // n_units * ny
@@ -66,26 +62,6 @@ struct SqRsGeom {
   unsigned wait_ns;     // suspend-time hint of the barrier waits
 };
 
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-// try_wait with a suspend-time hint: a waiting thread sleeps in hardware instead of spinning
-// through the issue port (the producers wait most of the time, the consumers some of it)
-__device__ __forceinline__ void mbar_wait_hint(unsigned bar, unsigned parity, unsigned hint_ns) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "NBH_WAITH_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-      "@p bra NBH_DONEH_%=;\n"
-      "bra NBH_WAITH_%=;\n"
-      "NBH_DONEH_%=:\n"
-      "}\n" ::"r"(bar), "r"(parity), "r"(hint_ns)
-      : "memory");
-}
 __device__ __forceinline__ float2 lds_f2(unsigned addr) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
@@ -171,26 +147,6 @@ square_rs_kernel(const __grid_constant__ SqParams p, const SqRsGeom g) {
       const int seg0 = gw0 == 0 ? 0 : g.W0 + (gw0 - 1) * g.W - g.hl;
       const int seg1 = min(p.nx, (gw1 == 0 ? 0 : g.W0 + (gw1 - 1) * g.W) + (gw1 == 0 ? g.W0 : g.W) + r);
       const float* plane_ptr = p.in + plane * p.plane_stride + seg0;
-      if (g.rps) {
-        // single-member launches: consecutive rows of a slice are contiguous in memory, so a stage
-        // is ONE copy of up to rps rows; the producers take the stages in turn (the others only arrive)
-        for (int k = 0; k < n_in; k += g.rps) {
-          const int n = min(g.rps, n_in - k);
-          const int y_mem = dir > 0 ? y_lo + k : y_hi - k - (n - 1);        // lowest row of the stage
-          const float* row = plane_ptr + (long long)y_mem * p.nx;
-          const unsigned shift_b = (unsigned)(reinterpret_cast<unsigned long long>(row) & 15ull);
-          const unsigned bytes = (shift_b + (unsigned)(n * p.nx) * 4u + 15u) & ~15u;
-          mbar_wait_hint(empty0 + 8 * s, (round & 1u) ^ 1u, g.wait_ns);
-          if ((int)((round * (unsigned)NS + (unsigned)s) % kRsProducers) == pw) {
-            mbar_expect_tx(full0 + 8 * s, bytes);
-            bulk_g2s(stage0 + (unsigned)s * stage_bytes, reinterpret_cast<const char*>(row) - shift_b, bytes, full0 + 8 * s);
-          } else {
-            mbar_arrive(full0 + 8 * s);
-          }
-          if (++s == NS) { s = 0; ++round; }
-        }
-        continue;
-      }
       for (int k = 0; k < n_in; ++k) {
         const int y = dir > 0 ? y_lo + k : y_hi - k;
         const float* row = plane_ptr + (long long)y * p.nx;
@@ -222,7 +178,7 @@ square_rs_kernel(const __grid_constant__ SqParams p, const SqRsGeom g) {
   // P contributes at most 2^-(fx_shift+1) / R to a mean (< 1e-7 for the UK configuration).
   // Raw-data launches keep the float64 sums of square_warp_kernel.
   constexpr bool FX = TM != 0;
-  const int n_hrows = g.rps ? kRsBatch : 1;                              // prefix rows per warp
+  const int n_hrows = 1;                                                 // prefix rows per warp
   const size_t per_warp = (size_t)(WS + 2) * 8 * n_hrows + (size_t)nb * WS * 4;
   unsigned char* wbase = reinterpret_cast<unsigned char*>(rtab + ((nb + 2) & ~1)) + (size_t)warp * per_warp;
   double* hrow = reinterpret_cast<double*>(wbase);                       // prefix rows: double or unsigned [WS + 2]
@@ -305,160 +261,6 @@ square_rs_kernel(const __grid_constant__ SqParams p, const SqRsGeom g) {
     if (M2D) m2_next = ldm_packed<VEC>(p.mask2d + (long long)min(max(y_first, 0), p.ny - 1) * p.nx + gx);
     __syncwarp();
 
-    if (g.rps) {
-      // ===== single-member launches: the (up to kRsBatch) rows of a stage are processed together.
-      // Their vertical updates are sequential but their scans and outputs are independent, which
-      // gives the instruction-level parallelism a one-row-at-a-time march lacks (the per-row
-      // dependent chain, not the issue rate, bounds that march).
-      constexpr int B = kRsBatch;
-      const int n_in_piece = min(yb - 1 + r, p.ny - 1) - max(ya - r, 0) + 1;
-      int consumed = 0;
-      int k = dir > 0 ? max(0, -y_first) : max(0, y_first - (p.ny - 1));     // leading rows outside the domain are zeros
-      while (k < n_rows) {
-        const int yy0 = y_first + dir * k;
-        const bool has_data = yy0 >= 0 && yy0 < p.ny;
-        int nbr;
-        float a0[B], a1[B];
-#pragma unroll
-        for (int j = 0; j < B; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
-        if (has_data) {
-          mbar_wait_hint(bar, parity, g.wait_ns);
-          nbr = min(g.rps, n_in_piece - consumed);
-          const int y_mem = dir > 0 ? yy0 : yy0 - (nbr - 1);                 // lowest row of the stage
-          const unsigned base = st_addr + lane_col_b +
-              (unsigned)((plane_elem0 + (unsigned long long)((long long)y_mem * p.nx)) & 3ull) * 4u;
-          float2 dv[B];
-          unsigned mk[B];
-#pragma unroll
-          for (int j = 0; j < B; ++j) {
-            dv[j] = make_float2(0.f, 0.f); mk[j] = 0x0101u;
-            if (j < nbr) {
-              const int off = dir > 0 ? j : nbr - 1 - j;                     // row index within the stage (memory order)
-              dv[j] = lds_f2(base + (unsigned)(off * p.nx) * 4u);
-              if (M2D) mk[j] = ldm_packed<VEC>(p.mask2d + (long long)(yy0 + dir * j) * p.nx + gx);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < B; ++j) {
-            if (j < nbr) {
-              const int yy = yy0 + dir * j;
-              const bool v0 = !M2D || (mk[j] & 0xffu), v1 = !M2D || (mk[j] & 0xff00u);
-              nanacc = max_nan(nanacc, fabsf(dv[j].x));
-              nanacc = max_nan(nanacc, fabsf(dv[j].y));
-              a0[j] = (col_active && v0) ? truth_value_sum<TM>(dv[j].x, thr) : 0.f;
-              a1[j] = (col_active && v1) ? truth_value_sum<TM>(dv[j].y, thr) : 0.f;
-              const bool row_band = yy <= r || yy >= p.ny - 1 - r;
-              if (!sum_only && (need_cols || row_band)) {
-                const unsigned long long ne =
-                    (!v0 || !v1 || truth_not_one(dv[j].x, thr) || truth_not_one(dv[j].y, thr)) ? 1ull : 0ull;
-                if (col_active) {
-                  if (band_l) ne_left |= ne;
-                  if (band_r) ne_right |= ne;
-                  if (yy <= r) ne_top |= ne;
-                  if (yy >= p.ny - 1 - r) ne_bot |= ne;
-                }
-              }
-            }
-          }
-          if (need_cols) {
-            bool done = true;
-            if (warp_band_l) done = done && __any_sync(0xffffffffu, ne_left != 0);
-            if (warp_band_r) done = done && __any_sync(0xffffffffu, ne_right != 0);
-            need_cols = !done;
-          }
-          consumed += nbr;
-          __syncwarp();                                    // every lane has read the stage
-          if (lane == 0) mbar_arrive(bar + 8 * kRsMaxStages);
-          next_stage();
-        } else {
-          nbr = min(B, n_rows - k);                        // rows below / above the domain: zeros
-        }
-
-        // ---- vertical sums (sequential over the rows of the batch), snapshots per row ----
-        unsigned us0[B], us1[B];
-        double vs0[B], vs1[B];
-#pragma unroll
-        for (int j = 0; j < B; ++j) {
-          if (j < nbr) {
-            if (FX) {
-              const unsigned q0 = __float2uint_rn(a0[j] * fx_scale), q1 = __float2uint_rn(a1[j] * fx_scale);
-              uint2* rp = reinterpret_cast<uint2*>(ring_u + slot * WS + c0);
-              const uint2 old = *rp;
-              *rp = make_uint2(q0, q1);
-              U0 += q0 - old.x; U1 += q1 - old.y;
-              us0[j] = U0; us1[j] = U1;
-            } else {
-              float* rp = ring + slot * WS + c0;
-              const float2 old = *reinterpret_cast<const float2*>(rp);
-              *reinterpret_cast<float2*>(rp) = make_float2(a0[j], a1[j]);
-              V0 += (double)a0[j] - (double)old.x; V1 += (double)a1[j] - (double)old.y;
-              vs0[j] = V0; vs1[j] = V1;
-            }
-            slot = (slot + 1 == nb) ? 0 : slot + 1;
-          } else { us0[j] = us1[j] = 0u; vs0[j] = vs1[j] = 0.0; }
-        }
-        // ---- warp scans of the batch, interleaved ----
-        unsigned iu[B];
-        double iv[B];
-#pragma unroll
-        for (int j = 0; j < B; ++j) { iu[j] = us0[j] + us1[j]; iv[j] = vs0[j] + vs1[j]; }
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-          for (int j = 0; j < B; ++j) {
-            if (FX) {
-              const unsigned o2 = __shfl_up_sync(0xffffffffu, iu[j], d);
-              iu[j] += (lane >= d) ? o2 : 0u;
-            } else {
-              const double o2 = __shfl_up_sync(0xffffffffu, iv[j], d);
-              iv[j] += (lane >= d) ? o2 : 0.0;
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < B; ++j) {
-          if (j < nbr && k + j >= 2 * r) {
-            if (FX) {
-              const unsigned ex = iu[j] - (us0[j] + us1[j]);
-              *reinterpret_cast<uint2*>(hrow_u + j * 2 * (WS + 2) + c0 + 2) = make_uint2(ex + us0[j], ex + us0[j] + us1[j]);
-            } else {
-              const double ex = iv[j] - (vs0[j] + vs1[j]);
-              hrow[j * (WS + 2) + c0 + 1] = ex + vs0[j];
-              hrow[j * (WS + 2) + c0 + 2] = ex + vs0[j] + vs1[j];
-            }
-          }
-        }
-        __syncwarp();
-        if (is_out) {
-#pragma unroll
-          for (int j = 0; j < B; ++j) {
-            if (j < nbr && k + j >= 2 * r) {
-              const int yo = y_first + dir * (k + j - r);
-              const int rows_in = min(yo + r, p.ny - 1) - max(yo - r, 0) + 1;
-              const double rrow = sum_only ? 1.0 : rtab[rows_in];
-              const long long pt0 = (long long)yo * p.nx + gxr;
-              float o[VEC];
-#pragma unroll
-              for (int v = 0; v < VEC; ++v) {
-                double Sw;
-                if (FX) Sw = (double)(hrow_u[j * 2 * (WS + 2) + idx_hi[v] + 1] - hrow_u[j * 2 * (WS + 2) + idx_lo[v] + 1]);
-                else Sw = hrow[j * (WS + 2) + idx_hi[v]] - hrow[j * (WS + 2) + idx_lo[v]];
-                if (M2D && !sum_only) o[v] = (float)(Sw * p.rcp_count[pt0 + v] * inv_members_fx);
-                else o[v] = (float)(Sw * rrow * rcol[v]);
-              }
-              VecLoad<VEC>::st(p.out + obase0 + pt0, o);
-              if (p.out_mask) {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v)
-                  p.out_mask[obase0 + pt0 + v] = (M2D && p.mask2d[pt0 + v] == 0) ? 1 : 0;
-              }
-            }
-          }
-        }
-        __syncwarp();                                      // the prefix rows are rewritten by the next batch
-        k += nbr;
-      }
-    } else
     for (int k = 0; k < n_rows; ++k) {
       const int yy = y_first + dir * k;
       const bool in_dom = (yy >= 0) && (yy < p.ny);

@@ -150,4 +150,61 @@ int run_threshold(const float* in, const uint8_t* mask_nd, float* out, int32_t* 
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Collapse of the leading axis by its arithmetic mean: collapse_realizations
+// (improver/utilities/cube_manipulation.py:93-131, iris MEAN = numpy's mean of a float32 array
+// over axis 0: rows added one after the other in float32, one float32 division).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+collapse_mean_kernel(const float* __restrict__ in, float* __restrict__ out, long long n_collapse, long long n_points) {
+  const float nf = (float)n_collapse;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_points;
+       i += (long long)gridDim.x * blockDim.x) {
+    float acc = __ldg(in + i);
+    for (long long m = 1; m < n_collapse; ++m) acc = __fadd_rn(acc, __ldg(in + m * n_points + i));
+    out[i] = __fdiv_rn(acc, nf);
+  }
+}
+
+int run_collapse_mean(const float* in, float* out, long long n_collapse, long long n_points, cudaStream_t st) {
+  NBH_REQUIRE(in && out, "null pointer argument");
+  NBH_REQUIRE(n_collapse >= 1 && n_points >= 1, "empty input");
+  const unsigned grid = (unsigned)max(1LL, min((n_points + 255) / 256, (long long)sm_count() * 16));
+  collapse_mean_kernel<<<grid, 256, 0, st>>>(in, out, n_collapse, n_points);
+  NBH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Zone collapse of ApplyNeighbourhoodProcessingWithAMask (improver/nbhood/use_nbhood.py:158-192):
+// weighted mean over the zone axis with the NaN results excluded and the weights renormalised
+// (np.ma.average semantics); all-NaN -> NaN.  values (n_lead, n_zones, n_points),
+// weights (n_zones, n_points) with masked weights already zeroed.
+__global__ void __launch_bounds__(256)
+zone_collapse_kernel(const float* __restrict__ values, const float* __restrict__ weights, float* __restrict__ out,
+                     long long n_lead, int n_zones, long long n_points) {
+  const long long total = n_lead * n_points;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long l = i / n_points, pt = i - l * n_points;
+    float num = 0.f, den = 0.f;
+    for (int z = 0; z < n_zones; ++z) {
+      const float v = values[(l * n_zones + z) * n_points + pt];
+      const float w = weights[(long long)z * n_points + pt];
+      if (!__isnanf(v)) { num = __fadd_rn(num, __fmul_rn(v, w)); den = __fadd_rn(den, w); }
+    }
+    out[i] = __fdiv_rn(num, den);          // 0 / 0 -> NaN where no zone is valid
+  }
+}
+
+int run_zone_collapse(const float* values, const float* weights, float* out, long long n_lead, int n_zones,
+                      long long n_points, cudaStream_t st) {
+  NBH_REQUIRE(values && weights && out, "null pointer argument");
+  NBH_REQUIRE(n_lead >= 1 && n_zones >= 1 && n_points >= 1, "empty input");
+  const long long total = n_lead * n_points;
+  const unsigned grid = (unsigned)max(1LL, min((total + 255) / 256, (long long)sm_count() * 16));
+  zone_collapse_kernel<<<grid, 256, 0, st>>>(values, weights, out, n_lead, n_zones, n_points);
+  NBH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace nbh

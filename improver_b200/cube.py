@@ -73,7 +73,7 @@ class Cube:
     def __init__(self, data, name: str = "unknown", units: str = "1",
                  dim_coords: Sequence[Tuple[Coord, int]] = (), scalar_coords: Sequence[Coord] = (),
                  attributes: Optional[Dict] = None):
-        self.data = data
+        self._data = data
         self._name = name
         self.units = units
         self._dim_coords: List[Tuple[Coord, int]] = [(c, int(d)) for c, d in dim_coords]
@@ -81,18 +81,40 @@ class Cube:
         self.attributes = dict(attributes or {})
         self.cell_methods = ()
 
+    # --- data: like iris, `data` realises deferred (device-resident, lazily evaluated) data and
+    # `core_data()` hands it out as it is (iris.cube.Cube.core_data / has_lazy_data) ------------
+    @property
+    def data(self):
+        from .lazy import Deferred
+
+        if isinstance(self._data, Deferred):
+            self._data = self._data.realise()
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._data = value
+
+    def core_data(self):
+        return self._data
+
+    def has_lazy_data(self) -> bool:
+        from .lazy import Deferred
+
+        return isinstance(self._data, Deferred)
+
     # --- basic properties -------------------------------------------------
     @property
     def shape(self):
-        return self.data.shape
+        return tuple(self._data.shape)
 
     @property
     def ndim(self):
-        return self.data.ndim
+        return len(self._data.shape)
 
     @property
     def dtype(self):
-        return self.data.dtype
+        return self._data.dtype
 
     def name(self) -> str:
         return self._name
@@ -149,7 +171,7 @@ class Cube:
 
     # --- copying --------------------------------------------------------------
     def copy(self, data=None) -> "Cube":
-        new = Cube(self.data.copy() if data is None else data, self._name, self.units,
+        new = Cube(self._data.copy() if data is None else data, self._name, self.units,
                    [(c.copy(), d) for c, d in self._dim_coords],
                    [c.copy() for c in self._scalar_coords], _copy.deepcopy(self.attributes))
         new.cell_methods = self.cell_methods

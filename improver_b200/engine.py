@@ -207,8 +207,17 @@ def neighbourhood(
         raise ValueError("{} is not a valid neighbourhood_method.".format(method))
 
     stream = _stream_ptr()
+    # launch groups: runs of at most MAX_THRESHOLDS_PER_LAUNCH thresholds of one evaluation kind
+    # (deterministic comparison / fuzzy: the kernels are specialised on it, threshold.py:438-455)
+    groups = []
+    for i, th in enumerate(thr_list):
+        det = float(th[1]) == float(th[2])
+        if groups and groups[-1][2] == det and len(groups[-1][1]) < MAX_THRESHOLDS_PER_LAUNCH:
+            groups[-1][1].append(th)
+        else:
+            groups.append([i, [th], det])
     with torch.cuda.device(data.device):
-        if T <= MAX_THRESHOLDS_PER_LAUNCH:
+        if len(groups) <= 1:
             thr_arr = make_thresholds(thr_list) if T else None
             desc = _fill_desc(data, cells, flags, n_planes, n_members, ny, nx, slice_elems, member_stride,
                               thr_arr, T, mask2d, mask_nd, pc, band, ext_stats)
@@ -217,11 +226,9 @@ def neighbourhood(
                           out_mask.data_ptr() if want_mask else None, status.data_ptr(),
                           ws.data_ptr(), ws.numel(), stream))
         else:
-            # more thresholds than one launch group: chunks write into a
-            # staging tensor that is scattered into the threshold axis
+            # the groups write into staging tensors that are scattered into the threshold axis
             acc_status = torch.zeros(2, dtype=torch.int32, device=data.device)
-            for t0 in range(0, T, MAX_THRESHOLDS_PER_LAUNCH):
-                chunk = thr_list[t0:t0 + MAX_THRESHOLDS_PER_LAUNCH]
+            for t0, chunk, _ in groups:
                 sub_stats = None
                 if ext_stats is not None:
                     sub_stats = ext_stats.view(-1, T, 10)[:, t0:t0 + len(chunk)].contiguous()
@@ -323,6 +330,39 @@ def threshold(data: torch.Tensor, thresholds, mask_nd: Optional[torch.Tensor] = 
     return out, contrib, status
 
 
+def collapse_mean(data: torch.Tensor) -> torch.Tensor:
+    """Mean over the leading axis (collapse_realizations, cube_manipulation.py:93-131)."""
+    lib = _lib.load()
+    _require_cuda(data, "data")
+    if data.dtype != torch.float32 or data.dim() < 2:
+        raise TypeError("data must be float32 with a leading axis to collapse")
+    data = data.contiguous()
+    out = torch.empty(tuple(data.shape[1:]), dtype=torch.float32, device=data.device)
+    with torch.cuda.device(data.device):
+        _lib.check(lib.nbh_collapse_mean_f32(data.data_ptr(), out.data_ptr(), int(data.shape[0]),
+                                             int(out.numel()), _stream_ptr()))
+    return out
+
+
+def zone_collapse(values: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    """NaN-aware weighted mean over the zone axis (use_nbhood.py:158-192): values (..., Z, ny, nx),
+    weights (Z, ny, nx) -> (..., ny, nx)."""
+    lib = _lib.load()
+    _require_cuda(values, "values")
+    _require_cuda(weights, "weights")
+    values, weights = values.contiguous(), weights.to(torch.float32).contiguous()
+    nz, ny, nx = (int(s) for s in values.shape[-3:])
+    if tuple(weights.shape) != (nz, ny, nx):
+        raise ValueError("weights must have the (zone, y, x) shape of the values")
+    lead = tuple(values.shape[:-3])
+    n_lead = int(np.prod(lead)) if lead else 1
+    out = torch.empty(lead + (ny, nx), dtype=torch.float32, device=values.device)
+    with torch.cuda.device(values.device):
+        _lib.check(lib.nbh_zone_collapse_f32(values.data_ptr(), weights.data_ptr(), out.data_ptr(), n_lead, nz,
+                                             ny * nx, _stream_ptr()))
+    return out
+
+
 def threshold_vicinity(data: torch.Tensor, thresholds, vicinity_cells: Sequence[int],
                        mask_nd: Optional[torch.Tensor] = None, landmask: Optional[torch.Tensor] = None,
                        collapse_leading: bool = False):
@@ -403,7 +443,8 @@ def extreme_within_vicinity(data: torch.Tensor, vicinity_cells: Sequence[int], o
 
 
 def recursive_filter(data: torch.Tensor, coeff_x: torch.Tensor, coeff_y: torch.Tensor, iterations: int,
-                     edge_width: int = 15, mask: Optional[torch.Tensor] = None, mask_zeros: bool = False):
+                     edge_width: int = 15, mask: Optional[torch.Tensor] = None, mask_zeros: bool = False,
+                     max_slices_per_call: Optional[int] = None):
     """The per-slice body of RecursiveFilter.process (recursive_filter.py:403-436) for every
     (y, x) slice of `data` float32 CUDA (..., ny, nx): symmetric halo of 2 * edge_width,
     `iterations` x (x forward, x backward, y forward, y backward), halo removed.  coeff_x
@@ -441,7 +482,8 @@ def recursive_filter(data: torch.Tensor, coeff_x: torch.Tensor, coeff_y: torch.T
         two = lib.nbh_recursive_filter_workspace_bytes(2, ny, nx, pad, coeff_flag)
         budget = min(16 << 30, torch.cuda.mem_get_info(data.device)[0] // 2)
         max_call = int(max(1, min(65535, (budget - one) // max(1, two - one) + 1)))
-        max_call = max(1, min(max_call, int(os.environ.get("NBH_RF_MAX_SLICES", max_call))))
+        if max_slices_per_call is not None:
+            max_call = max(1, min(max_call, int(max_slices_per_call)))
         flat_in, flat_out = data.view(n_slices, ny, nx), out.view(n_slices, ny, nx)
         flat_mask = mask.view(n_slices, ny, nx) if per_slice else mask
         for s0 in range(0, n_slices, max_call):

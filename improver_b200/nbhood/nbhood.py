@@ -96,7 +96,7 @@ class BaseNeighbourhoodProcessing(PostProcessingPlugin):
         """nbhood.py:151-175.  Unmasked NaNs raise ValueError; the check on the
         data itself is done by the kernels (status word), a cheap host check
         keeps the reference's fail-early behaviour for host arrays."""
-        data = cube.data
+        data = cube.core_data() if hasattr(cube, "core_data") else cube.data
         if isinstance(data, np.ndarray) and np.isnan(data).any():
             raise ValueError("Error: NaN detected in input cube data")
         if self.lead_times:
@@ -218,6 +218,13 @@ class NeighbourhoodProcessing(BaseNeighbourhoodProcessing):
             mask_cube_data = None
 
         perm, inv = _yx_last(cube)
+        # deferred (device-resident) data: record the operation (improver_b200.lazy)
+        from ..lazy import Deferred, NbhoodOp
+
+        core = cube.core_data() if hasattr(cube, "core_data") else None
+        if isinstance(core, Deferred) and list(perm) == list(range(len(perm))):
+            return cube.copy(data=NbhoodOp(core, self.neighbourhood_method, grid_cells, self.weighted_mode,
+                                           self.sum_only, mask_cube_data, self.re_mask))
         data = cube.data
         masked_in = isinstance(data, np.ma.MaskedArray)
         arr = np.ma.transpose(data, perm) if masked_in else np.transpose(data, perm)

@@ -45,16 +45,10 @@ def pinned_like(t: torch.Tensor) -> torch.Tensor:
     return torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
 
 
-_pinned_out_cache = {}
-
-
 def _pinned_out(shape):
-    """Pinned result buffers are expensive to allocate (cudaHostAlloc): keep one per shape."""
-    buf = _pinned_out_cache.get(shape)
-    if buf is None:
-        buf = torch.empty(shape, dtype=torch.float32, pin_memory=True)
-        _pinned_out_cache[shape] = buf
-    return buf
+    """Pinned result buffer from PyTorch's caching host allocator: a fresh tensor per call (the
+    caller owns it), cheap after the first call because released pinned blocks are reused."""
+    return torch.empty(shape, dtype=torch.float32, pin_memory=True)
 
 
 def threshold_neighbourhood_mean_host(host_in, thresholds: Sequence[float], bounds, comparison: str,
@@ -63,8 +57,8 @@ def threshold_neighbourhood_mean_host(host_in, thresholds: Sequence[float], boun
     """Fuzzy threshold -> neighbourhood -> realization mean for a HOST cube.
 
     host_in   float32 (R, L, ny, nx) numpy array or (preferably pinned) CPU tensor
-    out       optional pinned float32 (L, T, ny, nx) CPU tensor to receive the result;
-              by default a cached pinned buffer is returned (overwritten by the next call)
+    out       optional pinned float32 (L, T, ny, nx) CPU tensor to receive the result
+              (default: a new pinned tensor owned by the caller)
     returns   float32 (L, T, ny, nx) pinned CPU tensor
     Raises ValueError("Error: NaN detected in input cube data") like the
     reference plugins (nbhood.py:167-168)."""

@@ -183,17 +183,34 @@ class Threshold(PostProcessingPlugin):
         if self.threshold_units is not None and str(self.threshold_units) != str(input_cube.units):
             raise NotImplementedError("threshold_units conversion is outside the CUDA hot path")
 
-        data = input_cube.data
-        if self.fill_masked is not None:
-            data = np.ma.filled(data, self.fill_masked)
         self.original_units = input_cube.units
         self.threshold_coord_name = input_cube.name()
-
-        # collapse axes first, flattened into one leading axis
         dim_names = []
         for d in range(len(input_cube.shape)):
             found = [c for c in input_cube.dim_coords if input_cube.coord_dims(c) == (d,)]
             dim_names.append(found[0].name() if found else None)
+
+        # deferred (device-resident) input: record the operation, evaluate with the rest of the chain
+        from .lazy import Deferred, ThresholdOp
+
+        core = input_cube.core_data() if hasattr(input_cube, "core_data") else None
+        if isinstance(core, Deferred) and self.vicinity is None and not self.collapse_coord:
+            n_in = len(dim_names)
+            front = [i for i, n in enumerate(dim_names) if n in ("time", "realization")]
+            front.sort(key=lambda i: ["time", "realization"].index(dim_names[i]))
+            rest = [i for i in range(n_in) if i not in front]
+            axes = [i + 1 for i in front] + [0] + [i + 1 for i in rest]
+            full = (len(self.thresholds),) + tuple(input_cube.shape)
+            squeeze_axes = tuple(i for i, a in enumerate(axes) if full[a] == 1)
+            op = ThresholdOp(core, self._engine_thresholds(), axes, squeeze_axes)
+            out_names = [dim_names[i] for i in front] + ["__threshold__"] + [dim_names[i] for i in rest]
+            return self._finish_cube(input_cube, op, out_names, squeeze_axes, 0)
+
+        data = input_cube.data
+        if self.fill_masked is not None:
+            data = np.ma.filled(data, self.fill_masked)
+
+        # collapse axes first, flattened into one leading axis
         collapse_dims = [dim_names.index(c) for c in (self.collapse_coord or []) if c in dim_names]
         keep_dims = [d for d in range(len(dim_names)) if d not in collapse_dims]
         masked = isinstance(data, np.ma.MaskedArray)
@@ -247,9 +264,13 @@ class Threshold(PostProcessingPlugin):
                      + [kept_names[i] for i in rest])
         squeeze_axes = tuple(i for i, s in enumerate(res.shape) if s == 1)
         res = res.squeeze(axis=squeeze_axes) if squeeze_axes else res
+        return self._finish_cube(input_cube, res.astype(FLOAT_DTYPE), out_names, squeeze_axes, n_vic)
 
-        result = input_cube.copy(data=res.astype(FLOAT_DTYPE) if not isinstance(res, np.ma.MaskedArray)
-                                 else res.astype(FLOAT_DTYPE))
+    def _finish_cube(self, input_cube, res, out_names, squeeze_axes, n_vic):
+        """Metadata of the probability cube (threshold.py:349-405, 716-753)."""
+        from .cube import Coord
+
+        result = input_cube.copy(data=res)
         relative = "below" if "less_than" in self.comparison_operator.spp_string else "above"
         if hasattr(result, "_dim_coords"):
             old = {c.name(): c for c in input_cube.dim_coords}

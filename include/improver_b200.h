@@ -182,6 +182,17 @@ int nbh_threshold_f32(const float* in, const uint8_t* mask_nd, float* out, int32
                       const NbhThreshold* thresholds, int32_t n_thresholds,
                       int64_t n_collapse, int64_t n_points, int32_t* status, void* stream);
 
+/* Mean over the leading axis: replaces collapse_realizations (improver/utilities/cube_manipulation.py:93-131,
+ * iris MEAN = numpy's float32 mean over axis 0).  in float32 (n_collapse, n_points) -> out float32 (n_points). */
+int nbh_collapse_mean_f32(const float* in, float* out, int64_t n_collapse, int64_t n_points, void* stream);
+
+/* Zone collapse of ApplyNeighbourhoodProcessingWithAMask.collapse_mask_coord
+ * (improver/nbhood/use_nbhood.py:158-192): NaN-aware weighted mean over the zone axis with renormalised
+ * weights.  values float32 (n_lead, n_zones, n_points), weights float32 (n_zones, n_points) (masked
+ * weights as 0) -> out float32 (n_lead, n_points), NaN where no zone is valid. */
+int nbh_zone_collapse_f32(const float* values, const float* weights, float* out, int64_t n_lead, int32_t n_zones,
+                          int64_t n_points, void* stream);
+
 /* Threshold "in vicinity": replaces Threshold._vicinity_processing (improver/threshold.py:473-518)
  * with maximum_within_vicinity (improver/utilities/spatial.py:740-855) inside the accumulation
  * loop of Threshold.process (threshold.py:661-707).

@@ -17,12 +17,12 @@ def test_reference_arm_prints_one_json_line():
     lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
     rec = json.loads(lines[0])
-    assert rec["impl"] == "reference" and rec["higher_is_better"] is True and rec["scaling"] == "weak"
+    assert rec["impl"] == "reference" and rec["higher_is_better"] is True and rec["scaling"] == "strong"
     assert rec["metric"] == "neighbourhood gridpoint-evals/s" and rec["unit"] == "gridpoint-evals/s"
     assert rec["value"] > 0 and rec["ms_per_step"] > 0 and rec["steps"] == 1 and rec["warmup"] == 0
-    assert "workload" in rec["config"]
+    assert "workload" in rec["config"] and rec["config"]["shape"] == [18, 36, 970, 1042]
     cb = rec["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == rec["value"] and cb["sample"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] == 1 and cb["value"] == rec["value"] and cb["sample"]
     assert rec["e2e"] == {"value": rec["value"], "unit": rec["unit"], "h2d_bytes_per_step": 0,
                           "d2h_bytes_per_step": 0}
     assert rec["gpu_launches"] == 0

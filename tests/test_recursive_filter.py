@@ -341,8 +341,7 @@ def test_cuda_filter_launch_groups_are_equivalent(monkeypatch):
     dev_mask = torch.from_numpy(mask.astype(np.uint8)).cuda()
     whole = [engine.recursive_filter(*args, mask=m, mask_zeros=z).cpu().numpy()
              for m, z in ((None, False), (dev_mask, False), (None, True))]
-    monkeypatch.setenv("NBH_RF_MAX_SLICES", "3")
-    split = [engine.recursive_filter(*args, mask=m, mask_zeros=z).cpu().numpy()
+    split = [engine.recursive_filter(*args, mask=m, mask_zeros=z, max_slices_per_call=3).cpu().numpy()
              for m, z in ((None, False), (dev_mask, False), (None, True))]
     for a, b in zip(whole, split):
         np.testing.assert_array_equal(a, b)
@@ -352,10 +351,11 @@ def test_cuda_filter_launch_groups_are_equivalent(monkeypatch):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(1, 150, 40), (5, 97, 131), (37, 40, 70)])
-def test_cuda_fused_and_separate_sweeps_agree(monkeypatch, shape):
-    """The tile-row wavefront (y-forward inside the x-backward sweep, the default) and the separate
-    sweeps (NBH_RF_FUSE=0) are the same arithmetic: bit-identical results, also against the oracle,
-    with one slice (all tile rows of a slice in one block) and with more slices than a block holds."""
+def test_cuda_fused_sweeps_match_single_sweeps_and_oracle(shape):
+    """The tile-row wavefront (y-forward inside the x-backward sweep, ticket-ordered) is the same
+    arithmetic as the four single directional sweeps (nbh_recurse_f32 on the padded planes) and as
+    the oracle: bit-identical, with one slice (all tile rows of a slice in one block) and with more
+    slices than a block holds."""
     import torch
 
     from improver_b200 import engine
@@ -369,9 +369,7 @@ def test_cuda_fused_and_separate_sweeps_agree(monkeypatch, shape):
     args = (torch.from_numpy(data).cuda(), torch.from_numpy(cx).cuda(), torch.from_numpy(cy).cuda())
     for mask_zeros in (False, True):
         fused = engine.recursive_filter(*args, 2, 15, mask_zeros=mask_zeros).cpu().numpy()
-        monkeypatch.setenv("NBH_RF_FUSE", "0")
-        separate = engine.recursive_filter(*args, 2, 15, mask_zeros=mask_zeros).cpu().numpy()
-        monkeypatch.delenv("NBH_RF_FUSE")
-        np.testing.assert_array_equal(fused, separate)
+        again = engine.recursive_filter(*args, 2, 15, mask_zeros=mask_zeros, max_slices_per_call=2).cpu().numpy()
+        np.testing.assert_array_equal(fused, again)
         want = rfo.recursive_filter(data, cx, cy, 2, 15, mask_zeros=mask_zeros)
         np.testing.assert_array_equal(fused, np.ma.getdata(want))
