@@ -287,6 +287,11 @@ def _numa_bind(local_rank: int, world: int):
         return {"policy": "failed", "error": type(exc).__name__}
 
 
+def _log(msg):
+    if os.environ.get("RANK", "0") == "0":
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def _events():
     import torch
 
@@ -397,10 +402,11 @@ def secondary_configs(dev, cube, sm_clock_mhz):
         for m, tag in ((None, ""), (land, "_mask")):
             ms, _ = _timed(lambda: engine.neighbourhood(d2, r, mask2d=m))
             kernel_ms = pipeline.time_main_kernel(lambda: engine.neighbourhood(d2, r, mask2d=m), reps=3)
-            out, _, st = engine.neighbourhood(d2[:2], r, mask2d=m)
+            out, _, st = engine.neighbourhood(d2, r, mask2d=m)           # the timed launch: last two slices checked
             engine.check_status(st)
+            out = out[-2:]
             ya, yb = 300 - r, 360 + r
-            sub = d2[:2, ya:yb, :90 + r].cpu().numpy()
+            sub = d2[-2:, ya:yb, :90 + r].cpu().numpy()
             subm = land_h[ya:yb, :90 + r] if m is not None else None
             exp = np.stack([np.ma.getdata(orc.neighbourhood(s_, subm, method="square", cells=r, re_mask=False))
                             for s_ in sub])[:, r:r + 60, :90]
@@ -416,12 +422,13 @@ def secondary_configs(dev, cube, sm_clock_mhz):
         nn = n if r <= 27 else 48
         dd = d2[:nn]
         ms, _ = _timed(lambda: engine.neighbourhood_land_sea(dd, r, land, method="circular"), min_s=0.1, warm=1)
-        out, st = engine.neighbourhood_land_sea(dd[:1], r, land, method="circular")
+        out, st = engine.neighbourhood_land_sea(dd, r, land, method="circular")     # the timed launch: last slice checked
         engine.check_status(st)
+        out = out[-1:]
         side = 12
         y0, x0 = 500, 480
         ya, yb, xa, xb = y0 - r, y0 + side + r, x0 - r, x0 + side + r
-        exp = orc.land_sea_neighbourhood(dd[:1, ya:yb, xa:xb].cpu().numpy(), land_h[ya:yb, xa:xb],
+        exp = orc.land_sea_neighbourhood(dd[-1:, ya:yb, xa:xb].cpu().numpy(), land_h[ya:yb, xa:xb],
                                          method="circular", cells=r)[:, r:r + side, r:r + side]
         gathered = nn * NY * NX * 2 * (2 * r + 1) * 4
         res[f"c2_r{r}"] = {
@@ -511,8 +518,12 @@ def scale_workload(dev, rank, world):
         torch.cuda.synchronize()
         engine.check_status(st)
         ms = maxrank(e0.elapsed_time(e1) / reps)
+        # the last slice of the share against a launch of that slice alone (bit for bit)
+        one, _, st = engine.neighbourhood(mine[-1:].contiguous(), 5, method=method, wrap_x=True)
+        engine.check_status(st)
         res[f"sharded_{method}"] = {"ms": ms, "value": S * GLOBAL_NY * GLOBAL_NX / ms * 1e3,
-                                    "hbm_algorithmic_GBs": 8 * S * GLOBAL_NY * GLOBAL_NX / ms / 1e6}
+                                    "hbm_algorithmic_GBs": 8 * S * GLOBAL_NY * GLOBAL_NX / ms / 1e6,
+                                    "last_slice_max_abs_vs_single_launch": float((out[-1] - one[0]).abs().max())}
     del out
     # y-band tiling: Sb slices, every rank a band of rows of all of them
     Sb = 48
@@ -603,6 +614,7 @@ def run_ours(args):
                                             collapse_members=True, out=out)
         return st
 
+    _log(f"{len(cubes)} cube(s) generated")
     warm = max(args.warmup, 3)
     for _ in range(warm):
         status = eager_step()
@@ -658,6 +670,7 @@ def run_ours(args):
     peak, peak_src = peaks()
     achieved = ALGO_BYTES_PER_CUBE / (kernel_ms * 1e-3) / 1e9
 
+    _log(f"device timing done: sustained {ms_sustained:.4f} ms/step, burst {ms_burst:.4f}, kernel {kernel_ms:.4f}")
     # ---- in-run check of the timed output against the oracle (one lead time of the first cycle) ----
     max_abs = None
     if rank == 0 and cubes and not args.no_cpu:
@@ -675,7 +688,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         res = _plugin_chain(host_in)
         ref = outs[0].cpu().numpy()
-        e2e_err = float(np.max(np.abs(np.asarray(res) - ref)))
+        e2e_err = float(np.max(np.abs(np.asarray(res).reshape(ref.shape) - ref)))
         del res
         barrier()
         ev0.record()
@@ -705,6 +718,7 @@ def run_ours(args):
                "limit": "PCIe host-to-device copy of the 2.62 GB cube per cycle"}
         del host_in
 
+    _log(f"e2e done: {e2e.get('value')}")
     # ---- multi-rank parity and the sharded configs[4] subset ----
     parity = None
     if world > 1 and not args.no_scale:
@@ -719,6 +733,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
         scale = scale_workload(dev, rank, world)
 
+    _log("scale / parity done")
     line = None
     if rank == 0:
         line = {
@@ -753,6 +768,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_configs:
         sm_clock = line["clocks"].get("sm_mhz")
         line["configs"] = secondary_configs(dev, cubes[0], sm_clock)
+        _log("secondary configs done")
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         kind, note = cpu_kind()

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libimprover_b200.so")
-SOURCES = ["nbh_capi.cu", "nbh_square.cu", "nbh_square_v1.cu", "nbh_square_v2.cu", "nbh_square_v4.cu", "nbh_square_w1.cu", "nbh_square_w2.cu", "nbh_square_w4.cu", "nbh_square_rs.cu", "nbh_circular.cu", "nbh_percentile.cu", "nbh_threshold.cu", "nbh_vicinity.cu", "nbh_recursive.cu", "nbh_tiling.cu", "nbh_square_box.cu"] + [f"nbh_square_box_r{r}.cu" for r in range(1, 9)]
+SOURCES = ["nbh_capi.cu", "nbh_square.cu", "nbh_square_v1.cu", "nbh_square_v2.cu", "nbh_square_v4.cu", "nbh_square_w1.cu", "nbh_square_w2.cu", "nbh_square_w4.cu", "nbh_square_rs.cu", "nbh_circular.cu", "nbh_percentile.cu", "nbh_threshold.cu", "nbh_vicinity.cu", "nbh_recursive.cu", "nbh_tiling.cu", "nbh_square_box.cu"] + [f"nbh_square_box_r{r}.cu" for r in range(1, 9)] + ["nbh_square_mt.cu", "nbh_square_vh.cu"] + [f"nbh_square_mt_r{r}.cu" for r in range(1, 9)]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
@@ -35,7 +35,7 @@ def _stale(target: str, deps) -> bool:
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
-    headers = [os.path.join(CSRC, "nbh_common.cuh"), os.path.join(CSRC, "nbh_square.cuh"), os.path.join(CSRC, "nbh_square_warp.cuh"), os.path.join(CSRC, "nbh_async.cuh"), os.path.join(CSRC, "nbh_square_rs.cuh"), os.path.join(CSRC, "nbh_square_box.cuh"), os.path.join(CSRC, "nbh_square_box.cu"), 
+    headers = [os.path.join(CSRC, "nbh_common.cuh"), os.path.join(CSRC, "nbh_square.cuh"), os.path.join(CSRC, "nbh_square_warp.cuh"), os.path.join(CSRC, "nbh_async.cuh"), os.path.join(CSRC, "nbh_square_rs.cuh"), os.path.join(CSRC, "nbh_square_box.cuh"), os.path.join(CSRC, "nbh_square_box.cu"), os.path.join(CSRC, "nbh_square_mt.cuh"), os.path.join(CSRC, "nbh_square_mt.cu"), 
                os.path.join(HERE, "..", "include", "improver_b200.h")]
     objs = []
     jobs = []

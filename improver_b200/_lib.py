@@ -82,6 +82,11 @@ def load() -> C.CDLL:
                                       C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.nbh_collapse_mean_f32.restype = C.c_int
     lib.nbh_collapse_mean_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    lib.nbh_boxsum_f64.restype = C.c_int
+    lib.nbh_boxsum_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_void_p]
+    lib.nbh_linear_map_f32.restype = C.c_int
+    lib.nbh_linear_map_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int64, C.c_void_p]
     lib.nbh_zone_collapse_f32.restype = C.c_int
     lib.nbh_zone_collapse_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64,
                                           C.c_void_p]
@@ -129,7 +134,7 @@ def check(rc: int) -> None:
 
 
 EXPORTED = ["nbh_version", "nbh_last_error", "nbh_device_info", "nbh_workspace_bytes", "nbh_slice_stats_f32",
-            "nbh_collapse_mean_f32", "nbh_zone_collapse_f32", "nbh_halo_pack", "nbh_halo_unpack", "nbh_halo_exchange", "nbh_halo_exchange_workspace_bytes",
+            "nbh_collapse_mean_f32", "nbh_zone_collapse_f32", "nbh_linear_map_f32", "nbh_boxsum_f64", "nbh_halo_pack", "nbh_halo_unpack", "nbh_halo_exchange", "nbh_halo_exchange_workspace_bytes",
             "nbh_square_f32", "nbh_circular_f32", "nbh_percentiles_f32",
             "nbh_percentiles_workspace_bytes", "nbh_threshold_f32", "nbh_threshold_vicinity_f32", "nbh_vicinity_f32",
             "nbh_recursive_filter_f32", "nbh_recursive_filter_workspace_bytes", "nbh_recurse_f32",

@@ -168,6 +168,8 @@ int run_threshold(const float*, const uint8_t*, float*, int32_t*, const NbhThres
                   long long, int32_t*, cudaStream_t);
 int run_slice_stats(const NbhDesc*, const float*, NbhSliceStats*, cudaStream_t);
 int run_collapse_mean(const float*, float*, long long, long long, cudaStream_t);
+int run_linear_map(const float*, float*, double, double, long long, cudaStream_t);
+int run_boxsum_f64(const double*, double*, long long, int, int, int, int, int, cudaStream_t);
 int run_zone_collapse(const float*, const float*, float*, long long, int, long long, cudaStream_t);
 int run_halo_pack(const float*, float*, float*, float*, long long, int, int, int, int, int, cudaStream_t);
 int run_halo_unpack(float*, const float*, const float*, long long, int, int, int, int, cudaStream_t);
@@ -358,6 +360,15 @@ int nbh_circular_f32(const NbhDesc* desc, const float* in, float* out, uint8_t* 
 
 int nbh_collapse_mean_f32(const float* in, float* out, int64_t n_collapse, int64_t n_points, void* stream) {
   return nbh::run_collapse_mean(in, out, n_collapse, n_points, static_cast<cudaStream_t>(stream));
+}
+
+int nbh_boxsum_f64(const double* in, double* out, int64_t n_slices, int32_t rows, int32_t cols, int32_t box_y,
+                   int32_t box_x, int32_t cumsum, void* stream) {
+  return nbh::run_boxsum_f64(in, out, n_slices, rows, cols, box_y, box_x, cumsum, static_cast<cudaStream_t>(stream));
+}
+
+int nbh_linear_map_f32(const float* in, float* out, double a, double b, int64_t n, void* stream) {
+  return nbh::run_linear_map(in, out, a, b, n, static_cast<cudaStream_t>(stream));
 }
 
 int nbh_zone_collapse_f32(const float* values, const float* weights, float* out, int64_t n_lead, int32_t n_zones,

@@ -276,7 +276,8 @@ template <typename PT> __device__ __forceinline__ PT warp_incl_scan(PT v, int la
   return v;
 }
 
-// one warp per (plane, row): member sum + inclusive prefix along x
+// one warp per (plane, row): member sum + inclusive prefix along x.  A lane owns four consecutive
+// elements of every 128-element chunk (lane-local prefix of four, one warp scan per chunk).
 template <typename PT, bool LS>
 __global__ void __launch_bounds__(256) circ_prefix_kernel(const CircGlobalParams p) {
   if (p.guarded && *p.guard == 0) return;
@@ -295,36 +296,55 @@ __global__ void __launch_bounds__(256) circ_prefix_kernel(const CircGlobalParams
   double ccarry = 0.0;
   float nanacc = 0.f;
   bool bad = false;
-  for (int x0 = 0; x0 < p.nx; x0 += 32) {
-    const int x = x0 + lane;
-    float P = 0.f, okf = 0.f;
-    bool land = true;
-    if (x < p.nx) {
-      const bool m2 = m2_row ? (m2_row[x] != 0) : true;
-      land = m2;
-      bool valid = LS ? true : m2, seen = true;
-      if (mnd_row) { seen = mnd_row[x] == 0; valid = valid && seen; }
-      for (int m = 0; m < p.n_members; ++m) {
-        const float d = __ldg(in_row + (long long)m * p.member_stride + x);
-        if (seen) nanacc = max_nan(nanacc, fabsf(d));
-        if (p.check_range && !(d >= 0.f && d <= 1.f)) bad = true;
-        const float tv = p.thr.mode ? truth_value(d, p.thr) : d;
-        P += valid ? tv : 0.f;
+  constexpr int E = 4;
+  for (int x0 = 0; x0 < p.nx; x0 += 32 * E) {
+    const int xb = x0 + lane * E;
+    PT q[E], q2[E];
+    double ok[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int x = xb + e;
+      float P = 0.f, okf = 0.f;
+      bool land = true;
+      if (x < p.nx) {
+        const bool m2 = m2_row ? (m2_row[x] != 0) : true;
+        land = m2;
+        bool valid = LS ? true : m2, seen = true;
+        if (mnd_row) { seen = mnd_row[x] == 0; valid = valid && seen; }
+        for (int m = 0; m < p.n_members; ++m) {
+          const float d = __ldg(in_row + (long long)m * p.member_stride + x);
+          if (seen) nanacc = max_nan(nanacc, fabsf(d));
+          if (p.check_range && !(d >= 0.f && d <= 1.f)) bad = true;
+          const float tv = p.thr.mode ? truth_value(d, p.thr) : d;
+          P += valid ? tv : 0.f;
+        }
+        okf = valid ? 1.f : 0.f;
       }
-      okf = valid ? 1.f : 0.f;
+      const PT v = CircAcc<PT>::cvt(P, p.fx_scale);
+      q[e] = LS ? (land ? v : (PT)0) : v;
+      q2[e] = (LS && !land) ? v : (PT)0;
+      ok[e] = (double)okf;
     }
-    const PT q = CircAcc<PT>::cvt(P, p.fx_scale);
-    const PT incl = warp_incl_scan<PT>(LS ? (land ? q : (PT)0) : q, lane);
-    if (x < p.nx) pre[x] = carry + incl;
+    // lane-local inclusive prefix, then the warp scan of the lane totals
+#pragma unroll
+    for (int e = 1; e < E; ++e) { q[e] += q[e - 1]; if (LS) q2[e] += q2[e - 1]; ok[e] += ok[e - 1]; }
+    const PT incl = warp_incl_scan<PT>(q[E - 1], lane);
+    const PT off = carry + (incl - q[E - 1]);
+#pragma unroll
+    for (int e = 0; e < E; ++e) if (xb + e < p.nx) pre[xb + e] = off + q[e];
     carry += __shfl_sync(0xffffffffu, incl, 31);
     if (LS) {
-      const PT incl2 = warp_incl_scan<PT>(land ? (PT)0 : q, lane);
-      if (x < p.nx) pre2[x] = carry2 + incl2;
+      const PT incl2 = warp_incl_scan<PT>(q2[E - 1], lane);
+      const PT off2 = carry2 + (incl2 - q2[E - 1]);
+#pragma unroll
+      for (int e = 0; e < E; ++e) if (xb + e < p.nx) pre2[xb + e] = off2 + q2[e];
       carry2 += __shfl_sync(0xffffffffu, incl2, 31);
     }
     if (cpre) {
-      const double cincl = warp_incl_scan<double>((double)okf, lane);
-      if (x < p.nx) cpre[x] = ccarry + cincl;
+      const double cincl = warp_incl_scan<double>(ok[E - 1], lane);
+      const double coff = ccarry + (cincl - ok[E - 1]);
+#pragma unroll
+      for (int e = 0; e < E; ++e) if (xb + e < p.nx) cpre[xb + e] = coff + ok[e];
       ccarry += __shfl_sync(0xffffffffu, cincl, 31);
     }
   }
@@ -421,7 +441,7 @@ circ_gather_kernel(const CircGlobalParams p, const __grid_constant__ CircWidths 
 // instead of L1 / L2); LAND_SEA stages the window of both planes.
 constexpr int kCircTW = 64;
 
-template <typename PT, bool LS, bool PW>
+template <typename PT, bool LS, bool PW, bool BOTH>
 __global__ void __launch_bounds__(256)
 circ_gather_tiled_kernel(const CircGlobalParams p, const __grid_constant__ CircWidths cw, int TH, int tiles_x,
                          int tiles_y) {
@@ -430,7 +450,7 @@ circ_gather_tiled_kernel(const CircGlobalParams p, const __grid_constant__ CircW
   extern __shared__ __align__(16) unsigned char smem_c[];
   const int r = p.r;
   const int TC = kCircTW + 2 * r + 1, TR = TH + 2 * r;
-  PT* tile = reinterpret_cast<PT*>(smem_c);            // [LS ? 2 : 1][TR][TC], col j <-> global col x0 - r - 1 + j
+  PT* tile = reinterpret_cast<PT*>(smem_c);            // [TR][TC], col j <-> global col x0 - r - 1 + j
 
   long long bid = blockIdx.x;
   const int tx = (int)(bid % tiles_x); bid /= tiles_x;
@@ -438,10 +458,25 @@ circ_gather_tiled_kernel(const CircGlobalParams p, const __grid_constant__ CircW
   const int b = (int)bid;
   const int x0 = tx * kCircTW, y0 = ty * TH;
   const long long per_plane = (long long)p.ny * p.nx;
-#pragma unroll
+  const int lx = threadIdx.x % kCircTW;
+  const int x = x0 + lx;
+  const long long plane = p.plane0 + b;
+  const int cshift = r + 1 - x0;                                // tile column of global column gc: gc + cshift
+  // land / sea launches: both planes staged side by side when they fit (BOTH), else one after the
+  // other in the same buffer; a sequential pass is skipped when the tile holds no output of its type
+  constexpr bool SEQ = LS && !BOTH;
+#pragma unroll 1
   for (int k = 0; k < (LS ? 2 : 1); ++k) {
+    PT* tl = tile + ((LS && BOTH && k == 1) ? (size_t)TR * TC : 0);
+    if (SEQ) {
+      bool mine = false;
+      for (int ly = threadIdx.x / kCircTW; ly < TH; ly += blockDim.x / kCircTW) {
+        const int y = y0 + ly;
+        if (y < p.ny && x < p.nx) mine = mine || ((p.mask2d[(long long)y * p.nx + x] == 0) == (k == 1));
+      }
+      if (!__syncthreads_or(mine ? 1 : 0)) continue;
+    }
     const PT* pre = reinterpret_cast<const PT*>(k ? p.prefix2 : p.prefix) + (long long)b * per_plane;
-    PT* tl = tile + (size_t)k * TR * TC;
 #pragma unroll 4
     for (int i = threadIdx.x; i < TR * TC; i += blockDim.x) {
       const int jr = i / TC, jc = i - jr * TC;
@@ -450,55 +485,54 @@ circ_gather_tiled_kernel(const CircGlobalParams p, const __grid_constant__ CircW
       if (p.flags & NBH_WRAP_X) tl[i] = wrap_prefix<PT>(pre + (long long)ys * p.nx, gc, p.nx);
       else tl[i] = gc < 0 ? (PT)0 : pre[(long long)ys * p.nx + min(gc, p.nx - 1)];
     }
-  }
-  __syncthreads();
-
-  const int lx = threadIdx.x % kCircTW;
-  const int x = x0 + lx;
-  if (x >= p.nx) return;
-  const long long plane = p.plane0 + b;
-  const int cshift = r + 1 - x0;                                // tile column of global column gc: gc + cshift
-  for (int ly = threadIdx.x / kCircTW; ly < TH; ly += blockDim.x / kCircTW) {
-    const int y = y0 + ly;
-    if (y >= p.ny) break;
-    const long long pt = (long long)y * p.nx + x;
-    const PT* tl = tile + ((LS && p.mask2d[pt] == 0) ? (size_t)TR * TC : 0);
-    acc_t S = 0;
-    if ((p.flags & NBH_WRAP_X) || (x - r - 1 >= -1 && x + r <= p.nx - 1)) {
-      // every span lies inside the row (or the axis is periodic): two loads and two adds per kernel row
-      const PT* row = tl + (size_t)ly * TC + cshift + x;
+    if (LS && BOTH && k == 0) continue;                     // stage the sea plane too, then one compute pass
+    __syncthreads();
+    if (x < p.nx) {
+      for (int ly = threadIdx.x / kCircTW; ly < TH; ly += blockDim.x / kCircTW) {
+        const int y = y0 + ly;
+        if (y >= p.ny) break;
+        const long long pt = (long long)y * p.nx + x;
+        const bool sea = LS && p.mask2d[pt] == 0;
+        if (SEQ && (sea != (k == 1))) continue;
+        const PT* tsel = (LS && BOTH) ? tile + (sea ? (size_t)TR * TC : 0) : tile;
+        acc_t S = 0;
+        if ((p.flags & NBH_WRAP_X) || (x - r - 1 >= -1 && x + r <= p.nx - 1)) {
+          // every span lies inside the row (or the axis is periodic): two loads and two adds per kernel row
+          const PT* row = tsel + (size_t)ly * TC + cshift + x;
 #pragma unroll 4
-      for (int dy = 0; dy <= 2 * r; ++dy) {
-        const int w = PW ? (int)cw.w[dy] : p.wtab[dy < r ? r - dy : dy - r];
-        S += (acc_t)(PT)(row[w] - row[-w - 1]);
-        row += TC;
-      }
-    } else {
-      for (int dy = -r; dy <= r; ++dy) {
-        const int w = PW ? (int)cw.w[dy + r] : p.wtab[dy < 0 ? -dy : dy];
-        const PT* row = tl + (size_t)(ly + r + dy) * TC + cshift;   // indexable by global column >= -1
-        const int lo = max(x - w, 0), hi = min(x + w, p.nx - 1);
-        PT s = row[hi] - row[lo - 1];
-        const int nl = lo - (x - w), nr = (x + w) - hi;             // replicated edge cells (mode="nearest")
-        if (nl > 0) s += (PT)nl * (row[0] - row[-1]);
-        if (nr > 0) s += (PT)nr * (row[p.nx - 1] - row[p.nx - 2]);
-        S += (acc_t)s;
+          for (int dy = 0; dy <= 2 * r; ++dy) {
+            const int w = PW ? (int)cw.w[dy] : p.wtab[dy < r ? r - dy : dy - r];
+            S += (acc_t)(PT)(row[w] - row[-w - 1]);
+            row += TC;
+          }
+        } else {
+          for (int dy = -r; dy <= r; ++dy) {
+            const int w = PW ? (int)cw.w[dy + r] : p.wtab[dy < 0 ? -dy : dy];
+            const PT* row = tsel + (size_t)(ly + r + dy) * TC + cshift;   // indexable by global column >= -1
+            const int lo = max(x - w, 0), hi = min(x + w, p.nx - 1);
+            PT s2 = row[hi] - row[lo - 1];
+            const int nl = lo - (x - w), nr = (x + w) - hi;             // replicated edge cells (mode="nearest")
+            if (nl > 0) s2 += (PT)nl * (row[0] - row[-1]);
+            if (nr > 0) s2 += (PT)nr * (row[p.nx - 1] - row[p.nx - 2]);
+            S += (acc_t)s2;
+          }
+        }
+        circ_store<PT>(p, S, 0.0, false, plane, pt, per_plane);
       }
     }
-    circ_store<PT>(p, S, 0.0, false, plane, pt, per_plane);
+    if (SEQ) __syncthreads();                                  // the buffer is restaged for the other plane
   }
 }
 
-// pick the tallest tile that fits; 0 = use the direct gather
+// pick the tallest tile that fits; 0 = use the direct gather.  Measured on B200: tiles pay while
+// several blocks fit on an SM and the staged window is well reused (a 200 KB tile per SM at r = 81
+// was 1.7 x SLOWER than the direct gather from L1 / L2).  n_tiles = 2: both land / sea planes at once.
 static int circ_tile_rows(int r, int nx, size_t elem, int n_tiles, size_t* smem) {
   if (nx < 3) return 0;
   for (int th : {64, 32, 16}) {
-    const size_t bytes = (size_t)n_tiles * (th + 2 * r) * (kCircTW + 2 * r + 1) * elem;
-    // worth it while a few blocks fit on an SM and the staged window is well reused
-    if (bytes <= 72u * 1024 && (size_t)(th + 2 * r) * (kCircTW + 2 * r + 1) <= (size_t)12 * th * kCircTW) {
-      *smem = bytes;
-      return th;
-    }
+    const size_t cells = (size_t)(th + 2 * r) * (kCircTW + 2 * r + 1);
+    const size_t bytes = (size_t)n_tiles * cells * elem;
+    if (bytes <= 72u * 1024 && cells <= (size_t)12 * th * kCircTW) { *smem = bytes; return th; }
   }
   return 0;
 }
@@ -507,14 +541,30 @@ template <typename PT, bool LS, bool PW>
 static int launch_circ_gather_t(const CircGlobalParams& g, const CircWidths& cw, int ny, int nx, bool allow_tile,
                                 cudaStream_t st) {
   size_t smem = 0;
-  const int th = (g.cprefix || !allow_tile) ? 0 : circ_tile_rows(g.r, nx, sizeof(PT), LS ? 2 : 1, &smem);
+  int th = 0;
+  bool both = false;
+  if (!g.cprefix && allow_tile) {
+    if (LS) {
+      // both planes side by side while a tall tile fits; else one buffer, the planes one after the other
+      th = circ_tile_rows(g.r, nx, sizeof(PT), 2, &smem);
+      both = th >= 32;
+      if (!both) th = 0;
+    }
+    if (th == 0) th = circ_tile_rows(g.r, nx, sizeof(PT), 1, &smem);
+  }
   if (th > 0) {
-    auto kern = circ_gather_tiled_kernel<PT, LS, PW>;
-    NBH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles_x = (nx + kCircTW - 1) / kCircTW, tiles_y = (ny + th - 1) / th;
     const long long blocks = (long long)tiles_x * tiles_y * g.n_batch;
     NBH_REQUIRE(blocks < (1LL << 31), "too many blocks");
-    kern<<<(unsigned)blocks, 256, smem, st>>>(g, cw, th, tiles_x, tiles_y);
+    if (both) {
+      auto kern = circ_gather_tiled_kernel<PT, LS, PW, true>;
+      NBH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<(unsigned)blocks, 256, smem, st>>>(g, cw, th, tiles_x, tiles_y);
+    } else {
+      auto kern = circ_gather_tiled_kernel<PT, LS, PW, false>;
+      NBH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<(unsigned)blocks, 256, smem, st>>>(g, cw, th, tiles_x, tiles_y);
+    }
   } else {
     const long long outs = (long long)g.n_batch * ny * nx;
     circ_gather_kernel<PT, LS, PW><<<(unsigned)((outs + 255) / 256), 256, 0, st>>>(g, cw);
@@ -702,6 +752,7 @@ int run_circular(const NbhDesc* d, const float* in, float* out, uint8_t* out_mas
         g.n_batch = (int)min((long long)w.batch, d->n_planes - p0);
         if (fx_ok) {
           CircGlobalParams f = g;
+          f.guarded = 0;                                       // the fixed-point pass itself always runs
           f.fx_scale = (float)(1u << fx_shift); f.fx_inv = 1.0 / (double)(1u << fx_shift);
           f.check_range = d->n_thresholds == 0 ? 1 : 0;      // raw data: speculative, verified by the pass itself
           if (launch_circ_pass<unsigned>(f, cw, d->ny, d->nx, true, st)) return 1;

@@ -130,7 +130,101 @@ __device__ __forceinline__ void select_group(const unsigned (&key)[KPL], const P
   }
 }
 
+// ---------------------------------------------------------------------------
+// Sort-based selection (windows of up to 32 * 16 keys): the warp sorts its N keys once — every
+// lane a sorted block of KPL keys, blocks ascending across lanes — and every requested order
+// statistic is then a plain lookup, so the cost no longer grows with the number of percentiles
+// (the reference's default asks for 15, improver/constants.py DEFAULT_PERCENTILES) and is about a
+// third of the bit-by-bit bisection's for five.
+//
+// Network: Batcher's bitonic sort with each lane as a "processor" holding a sorted block
+// (merge-split): local sort, then log2(32) * (log2(32) + 1) / 2 = 15 rounds in which a lane
+// exchanges its block with lane ^ j, keeps the lower (or upper) half of the union —
+// min(A_i, B_{K-1-i}) resp. max — and re-sorts its half.  Blocks of any length K are handled
+// with the arbitrary-n bitonic merge (K. Batcher / H. W. Lang): compare i with i + m for the
+// largest power of two m < n, then recurse on [0, m) and [m, n); it sorts V-shaped sequences
+// (descending then ascending).  The upper half is V-shaped; the lower half is its mirror image
+// (ascending then descending) and is merged with the comparator reversed, then read backwards.
+// ---------------------------------------------------------------------------
+template <bool ASC> __device__ __forceinline__ void pct_ce(unsigned& a, unsigned& b) {
+  const unsigned lo = min(a, b), hi = max(a, b);
+  a = ASC ? lo : hi;
+  b = ASC ? hi : lo;
+}
+__device__ __forceinline__ void pct_ce_dir(unsigned& a, unsigned& b, bool asc) {
+  const unsigned lo = min(a, b), hi = max(a, b);
+  a = asc ? lo : hi;
+  b = asc ? hi : lo;
+}
+__host__ __device__ constexpr int pct_pow2_below(int n) { int m = 1; while (m * 2 < n) m *= 2; return m; }
+
+template <int LO, int N, bool ASC, int KPL> struct PctMerge {
+  static __device__ __forceinline__ void run(unsigned (&k)[KPL]) {
+    constexpr int M = pct_pow2_below(N);
+#pragma unroll
+    for (int i = LO; i < LO + N - M; ++i) pct_ce<ASC>(k[i], k[i + M]);
+    PctMerge<LO, M, ASC, KPL>::run(k);
+    PctMerge<LO + M, N - M, ASC, KPL>::run(k);
+  }
+  static __device__ __forceinline__ void run_dir(unsigned (&k)[KPL], bool asc) {
+    constexpr int M = pct_pow2_below(N);
+#pragma unroll
+    for (int i = LO; i < LO + N - M; ++i) pct_ce_dir(k[i], k[i + M], asc);
+    PctMerge<LO, M, ASC, KPL>::run_dir(k, asc);
+    PctMerge<LO + M, N - M, ASC, KPL>::run_dir(k, asc);
+  }
+};
+template <int LO, bool ASC, int KPL> struct PctMerge<LO, 1, ASC, KPL> {
+  static __device__ __forceinline__ void run(unsigned (&)[KPL]) {}
+  static __device__ __forceinline__ void run_dir(unsigned (&)[KPL], bool) {}
+};
+template <int LO, bool ASC, int KPL> struct PctMerge<LO, 0, ASC, KPL> {
+  static __device__ __forceinline__ void run(unsigned (&)[KPL]) {}
+  static __device__ __forceinline__ void run_dir(unsigned (&)[KPL], bool) {}
+};
+template <int LO, int N, bool ASC, int KPL> struct PctSort {
+  static __device__ __forceinline__ void run(unsigned (&k)[KPL]) {
+    constexpr int M = N / 2;
+    PctSort<LO, M, !ASC, KPL>::run(k);
+    PctSort<LO + M, N - M, ASC, KPL>::run(k);
+    PctMerge<LO, N, ASC, KPL>::run(k);
+  }
+};
+template <int LO, bool ASC, int KPL> struct PctSort<LO, 1, ASC, KPL> {
+  static __device__ __forceinline__ void run(unsigned (&)[KPL]) {}
+};
+template <int LO, bool ASC, int KPL> struct PctSort<LO, 0, ASC, KPL> {
+  static __device__ __forceinline__ void run(unsigned (&)[KPL]) {}
+};
+
 template <int KPL>
+__device__ __forceinline__ void warp_sort_blocks(unsigned (&key)[KPL], int lane) {
+  PctSort<0, KPL, true, KPL>::run(key);
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const bool lower = ((lane & j) == 0) == ((lane & k) == 0);
+      unsigned other[KPL];
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) other[i] = __shfl_xor_sync(0xffffffffu, key[KPL - 1 - i], j);
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) key[i] = lower ? min(key[i], other[i]) : max(key[i], other[i]);
+      // upper half: V-shaped, merged ascending; lower half: its mirror image, merged descending
+      PctMerge<0, KPL, true, KPL>::run_dir(key, !lower);
+      if (KPL > 1) {
+#pragma unroll
+        for (int i = 0; i < KPL / 2; ++i) {
+          const unsigned a = key[i], b = key[KPL - 1 - i];
+          key[i] = lower ? b : a;
+          key[KPL - 1 - i] = lower ? a : b;
+        }
+      }
+    }
+  }
+}
+
+template <int KPL, bool SORT>
 __global__ void __launch_bounds__(256)
 percentile_kernel(const PctParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -138,6 +232,7 @@ percentile_kernel(const PctParams p) {
   const int SW = p.TW + 2 * r, SH = p.TH + 2 * r;
   unsigned* tile = reinterpret_cast<unsigned*>(smem_raw);      // [SH][SW] keys of the padded field
   int* offs = reinterpret_cast<int*>(tile + (size_t)SH * SW);  // [32*KPL] tile-relative offsets
+  unsigned* sorted = reinterpret_cast<unsigned*>(offs + 32 * KPL) + (threadIdx.x >> 5) * (32 * KPL);   // SORT: per warp
 
   long long bid = blockIdx.x;
   const int tx = (int)(bid % p.tiles_x); bid /= p.tiles_x;
@@ -185,9 +280,28 @@ percentile_kernel(const PctParams p) {
 #pragma unroll
     for (int j = 0; j < KPL; ++j) key[j] = my_off[j] >= 0 ? tile[base + my_off[j]] : 0xffffffffu;
 
-    // Percentiles are processed up to five at a time: their bisections are
-    // independent, so interleaving them hides the latency of the warp reductions.
     const long long obase = (s * p.n_pct * (long long)p.ny + y) * p.nx + x;
+    if (SORT) {
+      warp_sort_blocks<KPL>(key, lane);
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) sorted[lane * KPL + j] = key[j];
+      __syncwarp();
+      // lane q serves percentile q: numpy _lerp (float32) between the ranks k and k + 1
+      for (int q = lane; q < p.n_pct; q += 32) {
+        const int k = p.k_lo[q];
+        const float lo = key2f(sorted[k]);
+        const float hi = key2f(sorted[min(k + 1, p.N - 1)]);
+        const float t = p.gamma[q];
+        const float diff = __fsub_rn(hi, lo);
+        float res = __fadd_rn(lo, __fmul_rn(diff, t));
+        if (t >= 0.5f) res = __fsub_rn(hi, __fmul_rn(diff, __fsub_rn(1.0f, t)));
+        p.out[obase + (long long)q * p.ny * p.nx] = res;
+      }
+      __syncwarp();
+      continue;
+    }
+    // Bisection path (very large windows): percentiles are processed up to five at a time: their
+    // bisections are independent, so interleaving them hides the latency of the warp reductions.
     int q0 = 0;
     while (q0 < p.n_pct) {
       const int nu = min(5, p.n_pct - q0);
@@ -210,9 +324,10 @@ size_t percentiles_workspace_bytes(long long n_slices, int ny, int nx, int cells
   return pad + nb * nb * 4 + 256;
 }
 
-template <int KPL>
+template <int KPL, bool SORT>
 static int launch_pct(const PctParams& p, long long blocks, size_t smem, cudaStream_t st) {
-  auto kern = percentile_kernel<KPL>;
+  auto kern = percentile_kernel<KPL, SORT>;
+  if (SORT) smem += (size_t)8 * 32 * KPL * 4;           // per-warp sorted blocks
   NBH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)blocks, 256, smem, st>>>(p);
   NBH_CHECK_CUDA(cudaGetLastError());
@@ -271,17 +386,17 @@ int run_percentiles(const float* in, float* out, const float* pct, int n_pct, lo
   int pick = 72;
   for (int s : sizes) if (s >= kpl) { pick = s; break; }
   const size_t smem = (size_t)(p.TW + 2 * r) * (p.TH + 2 * r) * 4 + (size_t)32 * pick * 4;
-  ProfileScope prof(st);
+  ProfileScope prof(st, "nbh::percentile_kernel (warp merge-split sort / bisection)");
   switch (pick) {
-    case 1: return launch_pct<1>(p, blocks, smem, st);
-    case 2: return launch_pct<2>(p, blocks, smem, st);
-    case 4: return launch_pct<4>(p, blocks, smem, st);
-    case 7: return launch_pct<7>(p, blocks, smem, st);
-    case 10: return launch_pct<10>(p, blocks, smem, st);
-    case 16: return launch_pct<16>(p, blocks, smem, st);
-    case 24: return launch_pct<24>(p, blocks, smem, st);
-    case 40: return launch_pct<40>(p, blocks, smem, st);
-    default: return launch_pct<72>(p, blocks, smem, st);
+    case 1: return launch_pct<1, true>(p, blocks, smem, st);
+    case 2: return launch_pct<2, true>(p, blocks, smem, st);
+    case 4: return launch_pct<4, true>(p, blocks, smem, st);
+    case 7: return launch_pct<7, true>(p, blocks, smem, st);
+    case 10: return launch_pct<10, true>(p, blocks, smem, st);
+    case 16: return launch_pct<16, true>(p, blocks, smem, st);
+    case 24: return launch_pct<24, false>(p, blocks, smem, st);
+    case 40: return launch_pct<40, false>(p, blocks, smem, st);
+    default: return launch_pct<72, false>(p, blocks, smem, st);
   }
 }
 

@@ -14,6 +14,7 @@
 // scan, normalises by the valid-cell count and stores float32.
 #include "nbh_square_rs.cuh"
 #include "nbh_square_box.cuh"
+#include "nbh_square_mt.cuh"
 
 namespace nbh {
 
@@ -341,8 +342,14 @@ struct SqWorkspace {
   float* cnt_plane;
   uint16_t* tmp;
   void* box;
+  unsigned* vh;
   size_t total;
 };
+
+bool plan_square_vh(const NbhDesc& d, const float* in, int* fx_shift);
+size_t vh_workspace_bytes(const NbhDesc& d);
+int launch_square_vh(const SqParams& sp, const NbhDesc& d, int tm, int fx_shift, BoxStats* stats, unsigned* vplane,
+                     cudaStream_t st);
 
 static void carve_workspace(const NbhDesc& d, void* ws, SqWorkspace* w) {
   const size_t nslices = (size_t)d.n_planes * d.n_members * max(d.n_thresholds, 1);
@@ -357,6 +364,8 @@ static void carve_workspace(const NbhDesc& d, void* ws, SqWorkspace* w) {
   w->cnt_plane = reinterpret_cast<float*>(base + off); off = align_up(off + (size_t)d.ny * d.nx * 4, 256);
   w->box = base + off;
   if (d.n_members == 1) off = align_up(off + box_workspace_bytes((long long)nslices, d.ny, d.nx), 256);
+  w->vh = reinterpret_cast<unsigned*>(base + off);
+  if (d.n_members == 1 && d.cells > 8 && d.cells <= 63) off = align_up(off + vh_workspace_bytes(d), 256);
   w->total = off;
 }
 
@@ -471,17 +480,25 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
     tm_warp = kind;
   }
   // Kernel choice (no run-time knobs):
-  //   members (fused threshold -> box sum -> realization mean): square_rs_kernel, else the warp kernel;
+  //   members (fused threshold -> box sum -> realization mean): square_mt_kernel for two or more
+  //   thresholds (one read of the input per four thresholds), square_rs_kernel for one, else the warp kernel;
   //   single-member slices, radius <= 8: square_box_kernel (+ guarded clamp / float64 re-run);
+  //   single-member slices, radius 9 .. 63: square_v_kernel + square_h_kernel (same follow-ups);
   //   everything else (periodic x, odd widths, radius > 8): warp kernel; masked arrays and radii
   //   beyond a warp strip: block-cooperative kernel.
   SqBoxGeom bg;
   int box_grid = 0;
   size_t box_smem = 0;
   const bool use_box = !masknd && plan_square_box(*d, in, &bg, &box_grid, &box_smem);
+  int vh_shift = 0;
+  const bool use_vh = !use_box && !masknd && plan_square_vh(*d, in, &vh_shift);
+  SqMtGeom mg;
+  int mt_grid = 0;
+  size_t mt_smem = 0;
+  const bool use_mt = !use_box && !use_vh && !masknd && plan_square_mt(*d, in, &mg, &mt_grid, &mt_smem);
   SqRsGeom rg;
   int rs_grid = 0;
-  const bool use_rs = !use_box && use_warp && plan_square_rs(*d, in, &rg, &rs_grid);
+  const bool use_rs = !use_box && !use_vh && !use_mt && use_warp && plan_square_rs(*d, in, &rg, &rs_grid);
   const bool m2d = d->mask2d != nullptr;
   auto launch_exact = [&](const SqParams& pp) -> int {
     if (use_warp) {
@@ -513,6 +530,35 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
       SqParams pr = p;
       pr.redo = bw.redo;
       rc = launch_exact(pr);
+    }
+  } else if (use_vh) {
+    // single-member slices, radius 9 .. 63: two radius-independent passes (vertical running sums,
+    // horizontal prefix differences) over exact fixed point, chunked so the intermediate stays in L2
+    BoxWorkspace bw;
+    box_carve(w.box, nslices, d->ny, d->nx, &bw);
+    if (box_prepare(bw, nullptr, nslices, d->ny, d->nx, st)) return 1;
+    if (!sum_only && launch_edge_flags(p, tm, st)) return 1;
+    {
+      ProfileScope prof(st, "nbh::square_v_kernel + nbh::square_h_kernel (two-pass fixed point, L2-resident intermediate)");
+      rc = launch_square_vh(p, *d, tm_warp, vh_shift, bw.stats, w.vh, st);
+    }
+    if (rc) return rc;
+    if (box_finish(bw, p, d->ext_stats, tm, nslices, st)) return 1;
+    if (tm == 0) {
+      SqParams pr = p;
+      pr.redo = bw.redo;
+      rc = launch_exact(pr);
+    }
+  } else if (use_mt) {
+    // several thresholds: the input is read once per group of up to four thresholds
+    if (launch_edge_flags(p, tm, st)) return 1;
+    ProfileScope prof(st, "nbh::square_mt_kernel (row-streaming, (window x threshold) consumer warps)");
+    rc = 0;
+    for (int t0 = 0; t0 < d->n_thresholds && rc == 0; t0 += mg.n_thr) {
+      SqMtGeom gg = mg;
+      gg.t_base = t0;
+      gg.n_thr = min(mg.n_thr, d->n_thresholds - t0);
+      rc = launch_square_mt(p, gg, tm_warp, m2d, mt_grid, mt_smem, st);
     }
   } else if (use_rs) {
     ProfileScope prof(st, "nbh::square_rs_kernel (row-streaming, bulk-copy staged rows)");

@@ -50,14 +50,15 @@ bool plan_square_box(const NbhDesc& d, const float* in, SqBoxGeom* g, int* grid,
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (smem_max <= 0) smem_max = 227 * 1024;
-  const int n_windows_total = (d.nx + kBoxUseful - 1) / kBoxUseful;
+  const int useful = box_useful_cols(r);
+  const int n_windows_total = (d.nx + useful - 1) / useful;
   const int n_panels = (n_windows_total + kBoxMaxWindows - 1) / kBoxMaxWindows;
   const int n_windows = (n_windows_total + n_panels - 1) / n_panels;
   g->n_windows = n_windows; g->n_panels = n_panels; g->n_windows_total = n_windows_total;
   const int B = m2d ? kBoxBMasked : kBoxBPlain;
   g->B = B;
   g->contiguous = n_panels == 1 ? 1 : 0;
-  const int seg_cols = min(d.nx, n_windows * kBoxUseful + 2 * kBoxK);
+  const int seg_cols = min(d.nx, n_windows * useful + 2 * box_halo_lanes(r) * kBoxK);
   g->seg_pitch = (seg_cols + 3 + 3) / 4 * 4;
   const int rows_floats = g->contiguous ? (B * d.nx + 3 + 3) / 4 * 4 : B * g->seg_pitch;
   g->mask_off = rows_floats;

@@ -36,13 +36,18 @@
 
 namespace nbh {
 
-constexpr int kBoxMaxWindows = 6;            // consumer warps per block (1536 columns per panel)
 constexpr int kBoxProducers = 1;         // one thread issues a bulk copy every ~500 cycles: a stage of B rows
                                          // per 500 cycles is several times what the consumers can take
+#ifndef NBH_BOX_K
+#define NBH_BOX_K 4
+#endif
+constexpr int kBoxK = NBH_BOX_K;             // consecutive columns per lane (4 or 8)
+constexpr int kBoxWinCols = 32 * kBoxK;      // columns a warp loads
+constexpr int kBoxMaxWindows = kBoxK == 8 ? 6 : 10;   // consumer warps per block
 constexpr int kBoxThreads = (kBoxMaxWindows + kBoxProducers) * 32;
-constexpr int kBoxK = 8;                     // columns per lane
-constexpr int kBoxWinCols = 32 * kBoxK;      // 256
-constexpr int kBoxUseful = 30 * kBoxK;       // 240: lanes 1..30 produce outputs
+// halo lanes on each side of a window for radius r: the lanes whose columns only feed their neighbours
+__host__ __device__ constexpr int box_halo_lanes(int r) { return (r + kBoxK - 1) / kBoxK; }
+__host__ __device__ constexpr int box_useful_cols(int r) { return (32 - 2 * box_halo_lanes(r)) * kBoxK; }
 constexpr int kBoxMaxStages = 8;
 #ifndef NBH_BOX_BPLAIN
 #define NBH_BOX_BPLAIN 2
@@ -100,11 +105,47 @@ __device__ __forceinline__ void box_wait(unsigned bar, unsigned parity, unsigned
   else mbar_wait(bar, parity);
 }
 
+// K consecutive values of a lane (K = 4 or 8): 8-byte shared loads, 16-byte ring accesses
+template <int K> __device__ __forceinline__ void box_lds(unsigned addr, float* v) {
+  lds_f4(addr, v);
+  if (K == 8) lds_f4(addr + 16u, v + 4);
+}
+template <int K> __device__ __forceinline__ void box_ring_ld(unsigned ra, unsigned* o) {
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(ra) : "memory");
+  if (K == 8)
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]) : "r"(ra) : "memory");
+}
+template <int K> __device__ __forceinline__ void box_ring_st(unsigned ra, const unsigned* q) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]) : "memory");
+  if (K == 8)
+    asm volatile("st.shared.v4.u32 [%0+16], {%1, %2, %3, %4};" ::"r"(ra), "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7]) : "memory");
+}
+template <int K> __device__ __forceinline__ float box_max_nan(const float* v, float acc) {
+  acc = max3_nan(acc, v[0], v[1]);
+  acc = max3_nan(acc, v[2], v[3]);
+  if (K == 8) { acc = max3_nan(acc, v[4], v[5]); acc = max3_nan(acc, v[6], v[7]); }
+  return acc;
+}
+template <int K> __device__ __forceinline__ float box_min(const float* v, float acc) {
+  acc = min3f(acc, v[0], v[1]);
+  acc = min3f(acc, v[2], v[3]);
+  if (K == 8) { acc = min3f(acc, v[4], v[5]); acc = min3f(acc, v[6], v[7]); }
+  return acc;
+}
+template <int K> __device__ __forceinline__ float box_max(const float* v, float acc) {
+  acc = max3f(acc, v[0], v[1]);
+  acc = max3f(acc, v[2], v[3]);
+  if (K == 8) { acc = max3f(acc, v[4], v[5]); acc = max3f(acc, v[6], v[7]); }
+  return acc;
+}
+
 template <int R, int TM, bool M2D>
 __global__ void __launch_bounds__(kBoxThreads, 2)
 square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
   static_assert(R >= 1 && R <= 8, "compile-time radius of the shuffle window");
   constexpr int K = kBoxK, B = M2D ? kBoxBMasked : kBoxBPlain, NB = 2 * R + 1;
+  constexpr int HL = box_halo_lanes(R), USEFUL = box_useful_cols(R);
+  constexpr unsigned FULLBITS = (1u << K) - 1u;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int NS = g.n_stages, NW = g.n_windows;
@@ -144,8 +185,8 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
       const int y_lo = max(ya - R, 0), y_hi = min(yb - 1 + R, p.ny - 1);
       const int n_in = y_hi - y_lo + 1;
       const int gw0 = panel * NW, gw1 = min(gw0 + NW, NBP) - 1;
-      const int seg0 = max(gw0 * kBoxUseful - K, 0);
-      const int seg1 = min(p.nx, gw1 * kBoxUseful - K + kBoxWinCols);
+      const int seg0 = max(gw0 * USEFUL - HL * K, 0);
+      const int seg1 = min(p.nx, gw1 * USEFUL - HL * K + kBoxWinCols);
       const float* plane_ptr = p.in + plane * p.plane_stride + seg0;
       const float* mask_ptr = M2D ? g.maskf + seg0 : nullptr;
       for (int k = 0; k < n_in; k += B) {
@@ -233,8 +274,8 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
     const int panel = (int)(task - unit * g.n_panels);
     const int gw = panel * NW + warp;                       // window index within the full row
     const int gw0 = panel * NW;
-    const int seg0 = max(gw0 * kBoxUseful - K, 0);          // first staged column of the panel
-    const int x0 = gw * kBoxUseful - K + lane * K;          // first column of this lane
+    const int seg0 = max(gw0 * USEFUL - HL * K, 0);          // first staged column of the panel
+    const int x0 = gw * USEFUL - HL * K + lane * K;          // first column of this lane
     const bool win_active = gw < NBP;
     // Columns of this lane inside the domain.  Every lane reads the eight values at its own
     // columns (a lane without any valid column reads the first staged group instead); what lies
@@ -243,10 +284,10 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
     unsigned okbits = 0;
 #pragma unroll
     for (int i = 0; i < K; ++i) okbits |= (win_active && x0 + i >= 0 && x0 + i < p.nx) ? (1u << i) : 0u;
-    const bool lane_full = okbits == 0xffu;
+    const bool lane_full = okbits == FULLBITS;
     const bool warp_edge = __any_sync(0xffffffffu, !lane_full);
     const int x_ld = okbits ? x0 : seg0;
-    const bool out_lane = lane >= 1 && lane <= 30 && okbits != 0;
+    const bool out_lane = lane >= HL && lane < 32 - HL && okbits != 0;
     const bool band_l = !sum_only && okbits && x0 <= R;
     const bool band_r = !sum_only && okbits && x0 + K - 1 >= p.nx - 1 - R;
     const long long plane = unit / p.n_thr;
@@ -262,8 +303,8 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
     // zero the ring (rows above the domain are zeros)
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
-      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(ring_u32 + (unsigned)q * (kBoxWinCols * 4u)), "r"(0u));
-      asm volatile("st.shared.v4.u32 [%0+16], {%1, %1, %1, %1};" ::"r"(ring_u32 + (unsigned)q * (kBoxWinCols * 4u)), "r"(0u));
+      const unsigned zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      box_ring_st<K>(ring_u32 + (unsigned)q * (kBoxWinCols * 4u), zero);
     }
     unsigned V[K];
 #pragma unroll
@@ -299,12 +340,8 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
             off = (unsigned)((e0 + (unsigned long long)(jj * p.nx)) & 3ull) * 4u + (unsigned)(jj * g.seg_pitch) * 4u;
             if (M2D) moff = (unsigned)((m0 + (unsigned long long)(jj * p.nx)) & 3ull) * 4u + (unsigned)(jj * g.seg_pitch) * 4u;
           }
-          lds_f4(st_addr + off + lane_col_b, &d[j][0]);
-          lds_f4(st_addr + off + lane_col_b + 16u, &d[j][4]);
-          if (M2D) {
-            lds_f4(st_addr + (unsigned)g.mask_off * 4u + moff + lane_col_b, &mk[j][0]);
-            lds_f4(st_addr + (unsigned)g.mask_off * 4u + moff + lane_col_b + 16u, &mk[j][4]);
-          }
+          box_lds<K>(st_addr + off + lane_col_b, &d[j][0]);
+          if (M2D) box_lds<K>(st_addr + (unsigned)g.mask_off * 4u + moff + lane_col_b, &mk[j][0]);
         }
         consumed += nbr;
         __syncwarp();                                       // every lane has read the stage
@@ -330,14 +367,11 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
 #pragma unroll
             for (int j = 0; j < B; ++j) {
               if (FULL || j < nbr) {
-                const float a = max3_nan(d[j][0], d[j][1], d[j][2]), b2 = max3_nan(d[j][3], d[j][4], d[j][5]);
-                const float c = max3_nan(d[j][6], d[j][7], a);
                 if (want_stats) {
-                  dmax = max3_nan(dmax, b2, c);
-                  const float e = min3f(d[j][0], d[j][1], d[j][2]), f = min3f(d[j][3], d[j][4], d[j][5]);
-                  dmin = min3f(dmin, min3f(d[j][6], d[j][7], e), f);
+                  dmax = box_max_nan<K>(d[j], dmax);
+                  dmin = box_min<K>(d[j], dmin);
                 } else {
-                  nanacc = max3_nan(nanacc, b2, c);
+                  nanacc = box_max_nan<K>(d[j], nanacc);
                 }
               }
             }
@@ -364,7 +398,11 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
           for (int i = 0; i < K; ++i) {
             float tv = truth_value_sum<TM>(d[j][i], thr);
             if (M2D) tv *= mk[j][i];
+#ifdef NBH_BOX_FAKE_CVT
+            q[j][i] = __float_as_uint(tv * fx_scale);      // timing experiment only: no conversion unit
+#else
             q[j][i] = __float2uint_rn(tv * fx_scale);
+#endif
           }
         }
         if (warp_edge || !has_data) {
@@ -406,16 +444,14 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
           for (int j = 0; j < B; ++j) {
             if (FULL || j < nbr) {
               const unsigned ra = ring_u32 + (unsigned)sl[j] * (kBoxWinCols * 4u);
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o[j][0]), "=r"(o[j][1]), "=r"(o[j][2]), "=r"(o[j][3]) : "r"(ra));
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(o[j][4]), "=r"(o[j][5]), "=r"(o[j][6]), "=r"(o[j][7]) : "r"(ra));
+              box_ring_ld<K>(ra, o[j]);
             }
           }
 #pragma unroll
           for (int j = 0; j < B; ++j) {
             if (FULL || j < nbr) {
               const unsigned ra = ring_u32 + (unsigned)sl[j] * (kBoxWinCols * 4u);
-              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(q[j][0]), "r"(q[j][1]), "r"(q[j][2]), "r"(q[j][3]) : "memory");
-              asm volatile("st.shared.v4.u32 [%0+16], {%1, %2, %3, %4};" ::"r"(ra), "r"(q[j][4]), "r"(q[j][5]), "r"(q[j][6]), "r"(q[j][7]) : "memory");
+              box_ring_st<K>(ra, q[j]);
 #pragma unroll
               for (int i = 0; i < K; ++i) { V[i] += q[j][i] - o[j][i]; Vs[j][i] = V[i]; }
             } else {
@@ -431,10 +467,8 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
             if (FULL || j < nbr) {
               const unsigned ra = ring_u32 + (unsigned)slot * (kBoxWinCols * 4u);
               unsigned o[K];
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(ra) : "memory");
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]) : "r"(ra) : "memory");
-              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(q[j][0]), "r"(q[j][1]), "r"(q[j][2]), "r"(q[j][3]) : "memory");
-              asm volatile("st.shared.v4.u32 [%0+16], {%1, %2, %3, %4};" ::"r"(ra), "r"(q[j][4]), "r"(q[j][5]), "r"(q[j][6]), "r"(q[j][7]) : "memory");
+              box_ring_ld<K>(ra, o);
+              box_ring_st<K>(ra, q[j]);
 #pragma unroll
               for (int i = 0; i < K; ++i) { V[i] += q[j][i] - o[i]; Vs[j][i] = V[i]; }
               slot = (slot + 1 == NB) ? 0 : slot + 1;
@@ -451,8 +485,12 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
             unsigned E[K + 2 * R];
 #pragma unroll
             for (int i = 0; i < R; ++i) {
-              E[i] = __shfl_up_sync(0xffffffffu, Vs[j][K - R + i], 1);
-              E[K + R + i] = __shfl_down_sync(0xffffffffu, Vs[j][i], 1);
+              // column x0 - (R - i): register dl * K - (R - i) of the lane dl to the left;
+              // column x0 + K + i: register i - (dr - 1) * K of the lane dr to the right
+              const int ol = R - i, dl = (ol + K - 1) / K;
+              const int orr = i + 1, dr = (orr + K - 1) / K;
+              E[i] = __shfl_up_sync(0xffffffffu, Vs[j][dl * K - ol], dl);
+              E[K + R + i] = __shfl_down_sync(0xffffffffu, Vs[j][i - (dr - 1) * K], dr);
             }
 #pragma unroll
             for (int i = 0; i < K; ++i) E[R + i] = Vs[j][i];
@@ -496,7 +534,11 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
                   nf = nrow * (float)(min(xo + R, p.nx - 1) - max(xo - R, 0) + 1);
                   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(nf));
                 }
+#ifdef NBH_BOX_FAKE_CVT
+                const float Sf = __uint_as_float(H[i]);
+#else
                 const float Sf = (float)H[i];
+#endif
                 const float q0 = Sf * rc;
                 const float rem = __fmaf_rn(-q0, nf, Sf);
                 o[i] = __fmaf_rn(rem, rc, q0);
@@ -505,16 +547,12 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
             if (out_lane) {
               if (lane_full) {
                 if (!sum_only) {
-                  omax = max3f(omax, max3f(o[0], o[1], o[2]), max3f(o[3], o[4], o[5]));
-                  omax = max3f(omax, o[6], o[7]);
-                  omin = min3f(omin, min3f(o[0], o[1], o[2]), min3f(o[3], o[4], o[5]));
-                  omin = min3f(omin, o[6], o[7]);
+                  omax = box_max<K>(o, omax);
+                  omin = box_min<K>(o, omin);
                 }
                 float* op = p.out + obase0 + pt0;
-                *reinterpret_cast<float2*>(op) = make_float2(o[0], o[1]);
-                *reinterpret_cast<float2*>(op + 2) = make_float2(o[2], o[3]);
-                *reinterpret_cast<float2*>(op + 4) = make_float2(o[4], o[5]);
-                *reinterpret_cast<float2*>(op + 6) = make_float2(o[6], o[7]);
+#pragma unroll
+                for (int i = 0; i < K; i += 2) *reinterpret_cast<float2*>(op + i) = make_float2(o[i], o[i + 1]);
               } else {
 #pragma unroll
                 for (int i = 0; i < K; ++i) {

@@ -175,6 +175,64 @@ int run_collapse_mean(const float* in, float* out, long long n_collapse, long lo
   return 0;
 }
 
+// Unit conversion of the data before thresholding (improver/threshold.py:430-431, cf_units on a
+// float32 array): out = float32(a * double(in) + b).
+__global__ void __launch_bounds__(256)
+linear_map_kernel(const float* __restrict__ in, float* __restrict__ out, double a, double b, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (float)__dadd_rn(__dmul_rn(a, (double)in[i]), b);
+}
+
+int run_linear_map(const float* in, float* out, double a, double b, long long n, cudaStream_t st) {
+  NBH_REQUIRE(in && out && n >= 1, "invalid argument");
+  const unsigned grid = (unsigned)max(1LL, min((n + 255) / 256, (long long)sm_count() * 16));
+  linear_map_kernel<<<grid, 256, 0, st>>>(in, out, a, b, n);
+  NBH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// boxsum (improver/utilities/neighbourhood_tools.py:129-211) in float64 for rectangular boxes:
+// out[i][j] = sum of in[i+1 .. i+by][j+1 .. j+bx] (cumsum = 1: `in` holds values, the window is
+// summed directly in float64, row by row) or the four-corner difference of an already cumulative
+// `in` (cumsum = 0).  in (n, H, W) -> out (n, H - by, W - bx).
+__global__ void __launch_bounds__(256)
+boxsum_f64_kernel(const double* __restrict__ in, double* __restrict__ out, long long n, int H, int W, int by, int bx,
+                  int cumsum) {
+  const int m = H - by, nn = W - bx;
+  const long long total = n * m * (long long)nn;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i / ((long long)m * nn);
+    const long long rem = i - s * (long long)m * nn;
+    const int y = (int)(rem / nn), x = (int)(rem - (long long)y * nn);
+    const double* p = in + s * (long long)H * W;
+    double r;
+    if (cumsum) {
+      r = 0.0;
+      for (int dy = 1; dy <= by; ++dy) {
+        double row = 0.0;
+        for (int dx = 1; dx <= bx; ++dx) row += p[(long long)(y + dy) * W + (x + dx)];
+        r += row;
+      }
+    } else {
+      r = p[(long long)(y + by) * W + (x + bx)] - p[(long long)y * W + (x + bx)] + p[(long long)y * W + x] -
+          p[(long long)(y + by) * W + x];
+    }
+    out[i] = r;
+  }
+}
+
+int run_boxsum_f64(const double* in, double* out, long long n, int H, int W, int by, int bx, int cumsum,
+                   cudaStream_t st) {
+  NBH_REQUIRE(in && out, "null pointer argument");
+  NBH_REQUIRE(n >= 1 && by >= 1 && bx >= 1 && H > by && W > bx, "box of %d x %d does not fit a %d x %d array", by, bx, H, W);
+  const long long total = n * (long long)(H - by) * (W - bx);
+  const unsigned grid = (unsigned)max(1LL, min((total + 255) / 256, (long long)sm_count() * 32));
+  boxsum_f64_kernel<<<grid, 256, 0, st>>>(in, out, n, H, W, by, bx, cumsum);
+  NBH_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // Zone collapse of ApplyNeighbourhoodProcessingWithAMask (improver/nbhood/use_nbhood.py:158-192):
 // weighted mean over the zone axis with the NaN results excluded and the weights renormalised
 // (np.ma.average semantics); all-NaN -> NaN.  values (n_lead, n_zones, n_points),

@@ -18,6 +18,33 @@ _LENGTH = {"m": 1.0, "metres": 1.0, "metre": 1.0, "meters": 1.0, "km": 1000.0, "
 _TIME = {"s": 1.0, "seconds": 1.0, "second": 1.0, "minutes": 60.0, "hours": 3600.0, "hour": 3600.0}
 
 
+# linear unit conversions of the cube double (value_SI = scale * value + offset), grouped by quantity;
+# with real iris cubes cf_units does this (improver/threshold.py:430-431 `cube.convert_units`)
+_LINEAR_UNITS = {
+    "temperature": {"K": (1.0, 0.0), "kelvin": (1.0, 0.0), "degC": (1.0, 273.15), "celsius": (1.0, 273.15),
+                    "degrees_celsius": (1.0, 273.15), "degF": (5.0 / 9.0, 459.67 * 5.0 / 9.0)},
+    "speed": {"m s-1": (1.0, 0.0), "m/s": (1.0, 0.0), "km h-1": (1.0 / 3.6, 0.0), "knots": (0.514444444444444, 0.0),
+              "mm h-1": (1.0 / 3.6e6, 0.0), "mm s-1": (1e-3, 0.0), "mm/hr": (1.0 / 3.6e6, 0.0)},
+    "length": {"m": (1.0, 0.0), "metres": (1.0, 0.0), "km": (1000.0, 0.0), "mm": (1e-3, 0.0), "cm": (1e-2, 0.0),
+               "feet": (0.3048, 0.0), "ft": (0.3048, 0.0)},
+    "fraction": {"1": (1.0, 0.0), "%": (0.01, 0.0), "percent": (0.01, 0.0)},
+    "pressure": {"Pa": (1.0, 0.0), "hPa": (100.0, 0.0), "mbar": (100.0, 0.0), "kPa": (1000.0, 0.0)},
+}
+
+
+def linear_unit_map(unit: str, target: str):
+    """(a, b) with value_target = a * value_unit + b, or ValueError for units of different quantities."""
+    unit, target = str(unit), str(target)
+    if unit == target:
+        return 1.0, 0.0
+    for table in _LINEAR_UNITS.values():
+        if unit in table and target in table:
+            s1, o1 = table[unit]
+            s2, o2 = table[target]
+            return s1 / s2, (o1 - o2) / s2
+    raise ValueError(f"Unable to convert from '{unit}' to '{target}'.")
+
+
 class CoordinateNotFoundError(KeyError):
     pass
 

@@ -27,6 +27,15 @@ import torch
 import torch.distributed as dist
 
 
+def _world(group=None) -> int:
+    """World size; 1 when torch.distributed is not initialised (single-process use)."""
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def _rank(group=None) -> int:
+    return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+
+
 def shard_range(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:
     """Contiguous [start, stop) of `n_items` for `rank` (sizes differ by at most 1)."""
     if world_size < 1 or not (0 <= rank < world_size):
@@ -56,8 +65,8 @@ def exchange_halo_rows(band: torch.Tensor, cells: int, group=None) -> torch.Tens
     """Return `band` (..., rows, nx) extended by `cells` rows from each neighbouring rank.
     Rank 0 gets no top halo and the last rank no bottom halo (the domain-edge rule of the kernels
     applies there).  CUDA float32 tensors over NCCL go through the native one-call exchange."""
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
+    world = _world(group)
+    rank = _rank(group)
     rows = band.shape[-2]
     if world == 1:
         return band
@@ -109,8 +118,8 @@ def _exchange_native(band: torch.Tensor, cells: int, rank: int, world: int, comm
 
 def crop_own_rows(extended: torch.Tensor, cells: int, group=None) -> torch.Tensor:
     """Inverse of exchange_halo_rows on a result computed from the extended band."""
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
+    world = _world(group)
+    rank = _rank(group)
     lo = cells if rank > 0 else 0
     hi = extended.shape[-2] - (cells if rank < world - 1 else 0)
     return extended[..., lo:hi, :]
@@ -119,6 +128,8 @@ def crop_own_rows(extended: torch.Tensor, cells: int, group=None) -> torch.Tenso
 def allreduce_slice_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     """Combine int32 (slices, 10) statistics of the bands into those of the whole slices: even
     columns are minima, odd columns maxima (include/improver_b200.h NbhSliceStats)."""
+    if _world(group) == 1:
+        return stats
     mins = stats[:, 0::2].contiguous()
     maxs = stats[:, 1::2].contiguous()
     dist.all_reduce(mins, op=dist.ReduceOp.MIN, group=group)
@@ -139,8 +150,8 @@ def neighbourhood_y_tiled(band: torch.Tensor, cells: int, ny_global: int, y_offs
     reference's ones-trimming behaviour whose bounding boxes are global."""
     from . import engine
 
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
+    world = _world(group)
+    rank = _rank(group)
     ext = exchange_halo_rows(band, cells, group)
     m_ext = None
     if mask_band is not None:
@@ -173,8 +184,8 @@ def neighbourhood_sharded(data: torch.Tensor, cells: int, gather: bool = False, 
     compute path)."""
     from . import engine
 
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
+    world = _world(group)
+    rank = _rank(group)
     s0, s1 = shard_range(data.shape[0], world, rank)
     out, omask, status = engine.neighbourhood(data[s0:s1].contiguous(), cells, **kwargs)
     if not gather:
@@ -193,8 +204,8 @@ def percentiles_sharded(data: torch.Tensor, cells: int, percentiles, gather: boo
     (out (share or all, P, ny, nx), status, (s0, s1))."""
     from . import engine
 
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
+    world = _world(group)
+    rank = _rank(group)
     s0, s1 = shard_range(data.shape[0], world, rank)
     if s1 > s0:
         out, status = engine.neighbourhood_percentiles(data[s0:s1].contiguous(), cells, percentiles)
@@ -210,8 +221,8 @@ def percentiles_sharded(data: torch.Tensor, cells: int, percentiles, gather: boo
 
 
 def _all_gather_uneven(pieces, mine, group):
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
+    world = _world(group)
+    rank = _rank(group)
     for r in range(world):
         if r == rank:
             pieces[r].copy_(mine)

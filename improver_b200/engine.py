@@ -344,6 +344,38 @@ def collapse_mean(data: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def boxsum_f64(data: torch.Tensor, box_y: int, box_x: int, cumsum: bool = True) -> torch.Tensor:
+    """neighbourhood_tools.py:129-211 on float64 CUDA data (..., rows, cols) -> (..., rows - box_y,
+    cols - box_x)."""
+    lib = _lib.load()
+    _require_cuda(data, "data")
+    if data.dtype != torch.float64 or data.dim() < 2:
+        raise TypeError("data must be float64 with two trailing axes")
+    data = data.contiguous()
+    H, W = int(data.shape[-2]), int(data.shape[-1])
+    lead = tuple(data.shape[:-2])
+    n = int(np.prod(lead)) if lead else 1
+    out = torch.empty(lead + (H - box_y, W - box_x), dtype=torch.float64, device=data.device)
+    with torch.cuda.device(data.device):
+        _lib.check(lib.nbh_boxsum_f64(data.data_ptr(), out.data_ptr(), n, H, W, int(box_y), int(box_x),
+                                      1 if cumsum else 0, _stream_ptr()))
+    return out
+
+
+def linear_map(data: torch.Tensor, a: float, b: float) -> torch.Tensor:
+    """float32(a * double(data) + b): cf_units' conversion of a float32 array (threshold.py:430-431)."""
+    lib = _lib.load()
+    _require_cuda(data, "data")
+    if data.dtype != torch.float32:
+        raise TypeError("data must be float32")
+    data = data.contiguous()
+    out = torch.empty_like(data)
+    with torch.cuda.device(data.device):
+        _lib.check(lib.nbh_linear_map_f32(data.data_ptr(), out.data_ptr(), float(a), float(b), int(data.numel()),
+                                          _stream_ptr()))
+    return out
+
+
 def zone_collapse(values: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
     """NaN-aware weighted mean over the zone axis (use_nbhood.py:158-192): values (..., Z, ny, nx),
     weights (Z, ny, nx) -> (..., ny, nx)."""

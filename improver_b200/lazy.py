@@ -196,13 +196,19 @@ class CollapseOp(Deferred):
         if not isinstance(th, ThresholdOp) or not isinstance(th.src, Source):
             return None
         src = th.src
-        if th.squeeze_axes:
-            return None
-        if src.ndim == 4 and tuple(th.axes) == (2, 1, 0, 3, 4) and self.axis == 1:
+        # a single threshold: the reference squeezes the length-1 threshold axis (threshold.py:731)
+        one = len(th.thresholds) == 1
+        if src.ndim == 4 and tuple(th.axes) == (2, 1, 0, 3, 4) and self.axis == 1 and \
+                tuple(th.squeeze_axes) == ((2,) if one else ()):
             return src, th, nb
-        if src.ndim == 3 and tuple(th.axes) == (1, 0, 2, 3) and self.axis == 0:
+        if src.ndim == 3 and tuple(th.axes) == (1, 0, 2, 3) and self.axis == 0 and \
+                tuple(th.squeeze_axes) == ((1,) if one else ()):
             return src, th, nb
         return None
+
+    def _drop_threshold_axis(self, arr, th):
+        """(..., T, y, x) of the fused kernel -> the squeezed layout when T == 1."""
+        return arr.squeeze(-3) if len(th.thresholds) == 1 else arr
 
     def _compute_device(self):
         from . import engine
@@ -216,7 +222,7 @@ class CollapseOp(Deferred):
         out, _, status = engine.neighbourhood(dev, nb.cells, method=nb.method, mask2d=nb._mask_dev(dev.device),
                                               thresholds=th.thresholds, collapse_members=True)
         _check(status)
-        return out
+        return self._drop_threshold_axis(out, th)
 
     def _compute_host(self):
         fused = self._fusable()
@@ -230,7 +236,7 @@ class CollapseOp(Deferred):
                 host, [t[0] for t in th.thresholds], [(t[1], t[2]) for t in th.thresholds], th.thresholds[0][3],
                 nb.cells, method=nb.method, mask2d=nb.mask2d, out=self._out_buffer)
             arr = res.numpy()
-            return arr if src.ndim == 4 else arr[0]
+            return self._drop_threshold_axis(arr if src.ndim == 4 else arr[0], th)
         return super()._compute_host()
 
     _out_buffer = None      # optional pinned (L, T, ny, nx) CPU tensor receiving the fused host result

@@ -34,18 +34,16 @@ class ApplyNeighbourhoodProcessingWithAMask(PostProcessingPlugin):
     def _collapse(values: np.ndarray, weights) -> np.ndarray:
         """use_nbhood.py:158-192: weighted mean over the zone axis (axis -3),
         NaN results excluded and the weights renormalised; all-NaN -> NaN.
-        Masked weights (e.g. sea points) mask the result."""
+        Masked weights (e.g. sea points) mask the result.  One native kernel (nbh_zone_collapse_f32)."""
         import torch
+
+        from .. import engine
 
         w = np.ma.getdata(weights).astype(np.float32)
         wmask = np.ma.getmaskarray(weights)
-        v = torch.from_numpy(np.ascontiguousarray(values)).cuda()
+        v = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float32)).cuda()
         wt = torch.from_numpy(np.ascontiguousarray(np.where(wmask, 0.0, w).astype(np.float32))).cuda()
-        valid = ~torch.isnan(v)
-        wv = torch.where(valid, wt.expand_as(v), torch.zeros((), device=v.device))
-        num = (torch.where(valid, v, torch.zeros((), device=v.device)) * wv).sum(dim=-3)
-        den = wv.sum(dim=-3)
-        res = (num / den).cpu().numpy().astype(np.float32)          # 0/0 -> NaN where nothing is valid
+        res = engine.zone_collapse(v, wt).cpu().numpy()
         if wmask.any():
             all_masked = wmask.all(axis=0)
             res = np.ma.masked_array(res, np.broadcast_to(all_masked, res.shape))

@@ -146,9 +146,7 @@ class Threshold(PostProcessingPlugin):
 
         from . import engine
 
-        if self.threshold_units is not None and str(self.threshold_units) != str(getattr(cube, "units", "")):
-            raise NotImplementedError("threshold_units conversion is outside the CUDA hot path")
-        data = cube.data
+        data = self._in_threshold_units(cube, cube.data)
         masked = isinstance(data, np.ma.MaskedArray)
         raw = np.ascontiguousarray(np.ma.getdata(data), dtype=np.float32)
         mnd = None
@@ -162,6 +160,29 @@ class Threshold(PostProcessingPlugin):
         if masked and bounds[0] != bounds[1]:
             res = np.ma.masked_array(res, mask=np.ma.getmaskarray(data))
         return res.astype(FLOAT_DTYPE)
+
+    def _in_threshold_units(self, cube, data):
+        """threshold.py:430-431: the DATA are converted to the threshold units before the comparison
+        (the thresholds and fuzzy bounds stay as given).  cf_units converts float32 arrays as
+        float32(a * double(x) + b); the same linear map runs on the device (engine.linear_map)."""
+        if self.threshold_units is None or str(self.threshold_units) == str(getattr(cube, "units", "")):
+            return data
+        import torch
+
+        from . import engine
+        from .cube import linear_unit_map
+
+        if hasattr(cube, "_dim_coords"):
+            a, b = linear_unit_map(str(cube.units), str(self.threshold_units))
+        else:                                   # iris cube: let cf_units supply the two constants
+            unit = cube.units
+            b = float(unit.convert(0.0, self.threshold_units))
+            a = float(unit.convert(1.0, self.threshold_units)) - b
+        raw = np.ascontiguousarray(np.ma.getdata(data), dtype=np.float32)
+        conv = engine.linear_map(torch.from_numpy(raw).cuda(), a, b).cpu().numpy()
+        if isinstance(data, np.ma.MaskedArray):
+            conv = np.ma.masked_array(conv, np.ma.getmaskarray(data))
+        return conv
 
     # -- cube level --------------------------------------------------------------------
     def process(self, input_cube, landmask=None):
@@ -180,8 +201,6 @@ class Threshold(PostProcessingPlugin):
             raise ValueError("Cannot apply land-mask cube without in-vicinity processing")
         if self.collapse_coord and "percentile" in self.collapse_coord:
             raise NotImplementedError("percentile rebadging is outside the CUDA hot path")
-        if self.threshold_units is not None and str(self.threshold_units) != str(input_cube.units):
-            raise NotImplementedError("threshold_units conversion is outside the CUDA hot path")
 
         self.original_units = input_cube.units
         self.threshold_coord_name = input_cube.name()
@@ -194,7 +213,8 @@ class Threshold(PostProcessingPlugin):
         from .lazy import Deferred, ThresholdOp
 
         core = input_cube.core_data() if hasattr(input_cube, "core_data") else None
-        if isinstance(core, Deferred) and self.vicinity is None and not self.collapse_coord:
+        same_units = self.threshold_units is None or str(self.threshold_units) == str(input_cube.units)
+        if isinstance(core, Deferred) and self.vicinity is None and not self.collapse_coord and same_units:
             n_in = len(dim_names)
             front = [i for i, n in enumerate(dim_names) if n in ("time", "realization")]
             front.sort(key=lambda i: ["time", "realization"].index(dim_names[i]))
@@ -206,7 +226,7 @@ class Threshold(PostProcessingPlugin):
             out_names = [dim_names[i] for i in front] + ["__threshold__"] + [dim_names[i] for i in rest]
             return self._finish_cube(input_cube, op, out_names, squeeze_axes, 0)
 
-        data = input_cube.data
+        data = self._in_threshold_units(input_cube, input_cube.data)
         if self.fill_masked is not None:
             data = np.ma.filled(data, self.fill_masked)
 
@@ -274,7 +294,13 @@ class Threshold(PostProcessingPlugin):
         relative = "below" if "less_than" in self.comparison_operator.spp_string else "above"
         if hasattr(result, "_dim_coords"):
             old = {c.name(): c for c in input_cube.dim_coords}
-            thr_coord = Coord(np.array(self.thresholds, dtype=FLOAT_DTYPE), self.threshold_coord_name,
+            thr_points = np.array(self.thresholds, dtype=np.float64)
+            if self.threshold_units is not None and str(self.threshold_units) != str(input_cube.units):
+                # threshold.py:716-718: the coordinate is built in the threshold units and converted back
+                from .cube import linear_unit_map
+                a, b = linear_unit_map(str(self.threshold_units), str(input_cube.units))
+                thr_points = a * thr_points + b
+            thr_coord = Coord(thr_points.astype(FLOAT_DTYPE), self.threshold_coord_name,
                               str(input_cube.units), var_name="threshold",
                               attributes={"spp__relative_to_threshold": self.comparison_operator.spp_string})
             vic_coord = None

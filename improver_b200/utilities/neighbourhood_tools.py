@@ -77,22 +77,13 @@ def boxsum(data: np.ndarray, boxsize: Union[int, Tuple[int, int]], cumsum: bool 
     if pad_options:
         data = pad_boxsum(data, boxsize, **pad_options)
     m, n = data.shape[-2] - bi, data.shape[-1] - bj
-    if not cumsum:
-        # input already cumulative: only the four-corner difference remains
-        t = torch.from_numpy(np.ascontiguousarray(data)).cuda()
-        res = (t[..., bi:bi + m, bj:bj + n] - t[..., :m, bj:bj + n]
-               + t[..., :m, :n] - t[..., bi:bi + m, :n])
-        return res.cpu().numpy()
-    if bi != bj:
-        raise NotImplementedError("rectangular boxes are not supported by the CUDA box-sum kernel")
+    integer = issubclass(data.dtype.type, np.integer) or data.dtype == np.bool_
     if m <= 0 or n <= 0:
-        return np.zeros(data.shape[:-2] + (max(m, 0), max(n, 0)), dtype=data.dtype)
-    # window (i, j) of the reference covers padded rows i+1 .. i+bi: centre i + 1 + bi//2
-    h = bi // 2
-    dev = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).cuda()
-    out, _, status = engine.neighbourhood(dev, h, method="square", sum_only=True)
-    engine.check_status(status)
-    res = out[..., 1 + h:1 + h + m, 1 + h:1 + h + n].cpu().numpy()
-    if issubclass(data.dtype.type, np.integer) or data.dtype == np.bool_:
+        return np.zeros(data.shape[:-2] + (max(m, 0), max(n, 0)), dtype=np.int64 if integer else np.float64)
+    # float64 on the device like the reference's float64 summed-area table (any odd box, also
+    # rectangular); integer input stays exact (sums below 2^53) and comes back as int64
+    dev = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float64)).cuda()
+    res = engine.boxsum_f64(dev, bi, bj, cumsum=cumsum).cpu().numpy()
+    if integer:
         return np.rint(res).astype(np.int64)
-    return res.astype(np.float64)
+    return res

@@ -186,6 +186,17 @@ int nbh_threshold_f32(const float* in, const uint8_t* mask_nd, float* out, int32
  * iris MEAN = numpy's float32 mean over axis 0).  in float32 (n_collapse, n_points) -> out float32 (n_points). */
 int nbh_collapse_mean_f32(const float* in, float* out, int64_t n_collapse, int64_t n_points, void* stream);
 
+/* boxsum of the utility API (improver/utilities/neighbourhood_tools.py:129-211) in float64, any
+ * odd box (box_y, box_x): in float64 (n_slices, rows, cols) -> out float64 (n_slices, rows - box_y,
+ * cols - box_x); out[i][j] = sum of in[i+1 .. i+box_y][j+1 .. j+box_x] (cumsum = 1), or the
+ * four-corner difference of an already cumulative input (cumsum = 0). */
+int nbh_boxsum_f64(const double* in, double* out, int64_t n_slices, int32_t rows, int32_t cols, int32_t box_y,
+                   int32_t box_x, int32_t cumsum, void* stream);
+
+/* out = float32(a * double(in) + b): the unit conversion of the data into the threshold units
+ * (improver/threshold.py:430-431 `cube.convert_units`, cf_units on a float32 array). */
+int nbh_linear_map_f32(const float* in, float* out, double a, double b, int64_t n, void* stream);
+
 /* Zone collapse of ApplyNeighbourhoodProcessingWithAMask.collapse_mask_coord
  * (improver/nbhood/use_nbhood.py:158-192): NaN-aware weighted mean over the zone axis with renormalised
  * weights.  values float32 (n_lead, n_zones, n_points), weights float32 (n_zones, n_points) (masked

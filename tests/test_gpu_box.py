@@ -144,3 +144,82 @@ def test_box_kernel_band_origin_independence():
         part, _, st = engine.neighbourhood(_dev(sub), 5, band=band, ext_stats=stats)
         engine.check_status(st)
         assert torch.equal(part[:, y0 - a:y0 - a + (y1 - y0)], full[:, y0:y1])
+
+
+@pytest.mark.parametrize("shape,cells,n_thr", [((5, 2, 48, 70), 3, 5), ((18, 1, 60, 1042), 5, 4), ((3, 2, 40, 250), 8, 2),
+                                                ((4, 1, 33, 1400), 1, 3), ((6, 3, 24, 16), 2, 6)])
+def test_multi_threshold_fused_kernel_vs_oracle(shape, cells, n_thr):
+    """square_mt_kernel: several thresholds from one read of the input (members x thresholds),
+    with / without an external mask, slices that trigger the ones-trimming fix-up, wide rows
+    (x panels) and a remainder group of thresholds."""
+    from improver_b200 import engine
+
+    rng = np.random.default_rng(33 + n_thr)
+    data = rng.gamma(2.0, 1.5, shape).astype(np.float32)
+    data[1, 0] = 50.0                                        # an all-ones member (edge flags)
+    data[1, 0, :2, 4:9] = 0.1
+    thr = [0.5, 1.0, 2.0, 4.0, 6.0, 8.0][:n_thr]
+    bounds = orc.fuzzy_bounds_from_factor(thr, 0.7)
+    mask = (rng.random(shape[-2:]) < 0.8).astype(np.uint8)
+    for m in (None, mask):
+        exp = orc.threshold_square_mean(data, thr, bounds, ">", cells, mask=m)
+        out, _, status = engine.neighbourhood(_dev(data), cells, mask2d=_dev(m) if m is not None else None,
+                                              thresholds=[(t, b[0], b[1], ">") for t, b in zip(thr, bounds)],
+                                              collapse_members=True)
+        engine.check_status(status)
+        _close(out.cpu().numpy(), exp)
+    # deterministic comparison and a "less than" fuzzy threshold in one call (two launch groups)
+    mixed = [(1.0, 1.0, 1.0, ">="), (2.0, 2.0, 2.0, ">"), (2.0, 1.4, 2.6, "<"), (4.0, 3.0, 5.0, "<")]
+    out, _, status = engine.neighbourhood(_dev(data), cells, thresholds=mixed, collapse_members=True)
+    engine.check_status(status)
+    for k, (v, lo, hi, op) in enumerate(mixed):
+        exp = orc.threshold_square_mean(data, [v], [(lo, hi)], op, cells)
+        _close(out[:, k:k + 1].cpu().numpy(), exp)
+
+
+@pytest.mark.parametrize("cells", [9, 16, 27, 40])
+@pytest.mark.parametrize("shape", [(3, 130, 250), (2, 300, 1042), (2, 97, 64)])
+def test_two_pass_kernels_vs_oracle(cells, shape):
+    """square_v_kernel + square_h_kernel (single-member slices, radius 9 .. 63): plain, masked,
+    sum_only, thresholded, a slice that is not a probability field, ones-trimming slices, several
+    y segments (300 rows) and the range property of the clip."""
+    from improver_b200 import engine
+
+    if 2 * cells + 1 > min(shape[-2:]):
+        pytest.skip("window larger than the grid")
+    rng = np.random.default_rng(7 * cells + shape[-1])
+    data = rng.random(shape).astype(np.float32)
+    data[0] = 1.0
+    data[0, :3, 5:40] = 0.25                                  # all ones apart from an edge blob (trimming fix-up)
+    data[-1, shape[1] // 2:, shape[2] // 2:] = 0.0
+    mask = (rng.random(shape[-2:]) < 0.75).astype(np.uint8)
+    for m in (None, mask):
+        md = _dev(m) if m is not None else None
+        for sum_only in (False, True):
+            out, omask, st = engine.neighbourhood(_dev(data), cells, mask2d=md, sum_only=sum_only, want_mask=True)
+            engine.check_status(st)
+            exp = _oracle(data, m, cells, sum_only)
+            scale = float((2 * cells + 1) ** 2) if sum_only else 1.0
+            _close(out.cpu().numpy(), exp, ATOL * scale)
+            if not sum_only:
+                got = out.cpu().numpy()
+                for i in range(shape[0]):
+                    ok = ~np.isnan(got[i])
+                    assert got[i][ok].min() >= data[i].min() and got[i][ok].max() <= data[i].max()
+    temps = data.copy()
+    temps[1] = 280.0 + 5.0 * temps[1]
+    out, _, st = engine.neighbourhood(_dev(temps), cells)
+    engine.check_status(st)
+    exp = _oracle(temps, None, cells)
+    _close(out.cpu().numpy()[[0]], exp[[0]])
+    np.testing.assert_allclose(out.cpu().numpy()[1], exp[1], rtol=2e-7)
+    gam = rng.gamma(2.0, 1.5, shape).astype(np.float32)
+    thr = [(2.0, 1.4, 2.6, ">"), (1.0, 1.0, 1.0, ">=")]
+    out, _, st = engine.neighbourhood(_dev(gam), cells, thresholds=thr)
+    engine.check_status(st)
+    for k, (v, lo, hi, op) in enumerate(thr):
+        _close(out[:, k].cpu().numpy(), _oracle(orc.truth_value(gam, v, (lo, hi), op), None, cells))
+    const = np.full((2,) + shape[-2:], 0.3, dtype=np.float32)
+    out, _, st = engine.neighbourhood(_dev(const), cells)
+    engine.check_status(st)
+    np.testing.assert_array_equal(out.cpu().numpy(), const)

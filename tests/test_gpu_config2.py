@@ -142,3 +142,26 @@ def test_square_land_sea_fullsize_vs_oracle_crops(cells):
     if not ((sub == 1).all() or (sub == 0).all()):
         exp = orc.land_sea_neighbourhood(sub, land[ya:yb, xa:xb], method="square", cells=cells)
         np.testing.assert_allclose(got[:, y0:y1, x0:x1], exp[:, y0 - ya:y1 - ya, x0 - xa:x1 - xa], atol=ATOL)
+
+
+@pytest.mark.parametrize("cells,masked", [(5, False), (9, True)])
+def test_circular_many_slices_equal_single_slice_launches(cells, masked):
+    """More slices than one prefix batch holds (the float64 / fixed-point row prefixes of a batch of
+    planes live in a bounded workspace): every batch must be computed, raw and land-sea masked."""
+    from improver_b200 import engine
+
+    n = 75
+    dev = W.counter_uniform(0, n, W.UK, 9, "cuda")
+    land = torch.from_numpy((W.land_sea_mask() > 0).astype(np.uint8)).cuda() if masked else None
+    if masked:
+        out, st = engine.neighbourhood_land_sea(dev, cells, land, method="circular")
+    else:
+        out, _, st = engine.neighbourhood(dev, cells, method="circular")
+    engine.check_status(st)
+    for k in (0, 32, 33, 40, 65, 66, 74):
+        if masked:
+            one, st = engine.neighbourhood_land_sea(dev[k:k + 1].contiguous(), cells, land, method="circular")
+        else:
+            one, _, st = engine.neighbourhood(dev[k:k + 1].contiguous(), cells, method="circular")
+        engine.check_status(st)
+        assert torch.equal(out[k].nan_to_num(-1.0), one[0].nan_to_num(-1.0)), k

@@ -376,3 +376,25 @@ def test_meta_neighbourhood_degrees_as_complex_and_halo():
     assert trimmed.shape == (2, 18, 24)
     np.testing.assert_array_equal(np.ma.getdata(trimmed.data), np.ma.getdata(full.data)[:, 3:-3, 3:-3])
     np.testing.assert_array_equal(trimmed.coord(axis="x").points, full.coord(axis="x").points[3:-3])
+
+
+def test_threshold_units_converts_the_data_on_the_device():
+    """threshold.py:430-431, 716-718: thresholds given in other units than the cube's: the data
+    are converted (float32(a * double(x) + b) like cf_units), the threshold coordinate comes back
+    in the cube's units."""
+    from improver_b200.synthetic_data import set_up_variable_cube
+    from improver_b200.threshold import Threshold
+
+    rng = np.random.default_rng(17)
+    kelvin = (273.15 + 10.0 * rng.random((3, 12, 14))).astype(np.float32)
+    cube = set_up_variable_cube(kelvin, name="air_temperature", units="K")
+    res = Threshold(threshold_values=[2.0, 5.0], threshold_units="degC", comparison_operator=">")(cube)
+    celsius = (kelvin.astype(np.float64) - 273.15).astype(np.float32)
+    exp = np.stack([(celsius > np.float32(t)).astype(np.float32) for t in (2.0, 5.0)], axis=1)
+    np.testing.assert_array_equal(np.asarray(res.data), exp)
+    np.testing.assert_allclose(res.coord(var_name="threshold").points, [275.15, 278.15], rtol=1e-6)
+    assert str(res.coord(var_name="threshold").units) == "K"
+    fuzzy = Threshold(threshold_values=[5.0], fuzzy_factor=0.8, threshold_units="degC")(cube)
+    from oracle import nbhood_oracle as orc
+    want = orc.truth_value(celsius, 5.0, (4.0, 6.0), ">")
+    np.testing.assert_array_equal(np.asarray(fuzzy.data), want)
