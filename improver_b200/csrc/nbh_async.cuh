@@ -42,6 +42,21 @@ __device__ __forceinline__ void mbar_wait_hint(unsigned bar, unsigned parity, un
       "}\n" ::"r"(bar), "r"(parity), "r"(hint_ns)
       : "memory");
 }
+// producer-side wait: the producer thread has stages of slack, so it sleeps between tries instead
+// of taking issue slots from the math warps with a polling loop
+__device__ __forceinline__ void mbar_wait_backoff(unsigned bar, unsigned parity, unsigned sleep_ns) {
+  for (;;) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    __nanosleep(sleep_ns);
+  }
+}
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)

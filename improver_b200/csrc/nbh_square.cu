@@ -518,7 +518,7 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
     BoxWorkspace bw;
     box_carve(w.box, nslices, d->ny, d->nx, &bw);
     if (box_prepare(bw, d->mask2d, nslices, d->ny, d->nx, st)) return 1;
-    bg.stats = bw.stats; bg.maskf = bw.maskf;
+    bg.stats = bw.stats;
     {
       ProfileScope prof(st, "nbh::square_box_kernel (row-streaming, fixed-point, shuffle windows)");
       rc = launch_square_box(p, bg, tm_warp, m2d, box_grid, box_smem, st);

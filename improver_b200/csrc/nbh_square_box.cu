@@ -62,7 +62,11 @@ bool plan_square_box(const NbhDesc& d, const float* in, SqBoxGeom* g, int* grid,
   g->seg_pitch = (seg_cols + 3 + 3) / 4 * 4;
   const int rows_floats = g->contiguous ? (B * d.nx + 3 + 3) / 4 * 4 : B * g->seg_pitch;
   g->mask_off = rows_floats;
-  g->stage_floats = rows_floats * (m2d ? 2 : 1);
+  // uint8 mask rows behind the data rows: 16-byte copies of unaligned rows, one spare word for the
+  // aligned-word reads of the last lane
+  g->mask_pitch = (seg_cols + 15 + 15 + 4) / 16 * 16;
+  const int mask_bytes = g->contiguous ? (B * d.nx + 15 + 15 + 4) / 16 * 16 : B * g->mask_pitch;
+  g->stage_floats = rows_floats + (m2d ? mask_bytes / 4 : 0);
   const size_t ring = (size_t)n_windows * nb * kBoxWinCols * 4;
   const size_t fixed = 2 * kBoxMaxStages * 8 + ring + 128;
   // two blocks per SM when they fit with at least three stages each
@@ -73,7 +77,7 @@ bool plan_square_box(const NbhDesc& d, const float* in, SqBoxGeom* g, int* grid,
   g->n_stages = (int)min((size_t)kBoxMaxStages, (budget - fixed) / stage_b);
   *smem = fixed + (size_t)g->n_stages * stage_b;
   int shift = 0;
-  while (shift < 24 && (double)nb * nb * (double)(1u << (shift + 1)) < 4294967296.0) ++shift;
+  while (shift < 22 && (double)nb * nb * (double)(1u << (shift + 1)) < 4294967296.0) ++shift;   // <= 22: box_to_fixed
   g->fx_shift = shift;
   g->wait_ns = 0;
   g->rows_total = d.n_planes * (long long)max(d.n_thresholds, 1) * n_panels * d.ny;
@@ -182,7 +186,8 @@ size_t box_workspace_bytes(long long n_units, int ny, int nx) {
   const size_t a = ((size_t)n_units * sizeof(BoxStats) + 255) / 256 * 256;
   const size_t b = ((size_t)n_units * 4 + 255) / 256 * 256;
   const size_t c = ((size_t)n_units * 8 + 255) / 256 * 256;
-  return a + 2 * b + c + 512 + ((size_t)ny * nx * 4 + 255) / 256 * 256;
+  (void)ny; (void)nx;
+  return a + 2 * b + c + 512;
 }
 
 void box_carve(void* ws, long long n_units, int ny, int nx, BoxWorkspace* w) {
@@ -194,21 +199,13 @@ void box_carve(void* ws, long long n_units, int ny, int nx, BoxWorkspace* w) {
   w->range = reinterpret_cast<float2*>(base + off); off += ((size_t)n_units * 8 + 255) / 256 * 256;
   w->n_clamp = reinterpret_cast<int*>(base + off); off += 256;
   w->n_redo = reinterpret_cast<int*>(base + off); off += 256;
-  w->maskf = reinterpret_cast<float*>(base + off);
-}
-
-__global__ void box_mask_float_kernel(const uint8_t* mask, float* mf, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) mf[i] = mask[i] ? 1.f : 0.f;
+  (void)ny; (void)nx;
 }
 
 int box_prepare(const BoxWorkspace& w, const uint8_t* mask2d, long long n_units, int ny, int nx, cudaStream_t st) {
   box_init_kernel<<<(unsigned)((n_units + 255) / 256), 256, 0, st>>>(w.stats, w.redo, w.range, w.n_redo, n_units);
   NBH_CHECK_CUDA(cudaMemsetAsync(w.n_clamp, 0, sizeof(int), st));
-  if (mask2d) {
-    const long long n = (long long)ny * nx;
-    box_mask_float_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mask2d, w.maskf, n);
-  }
+  (void)mask2d; (void)ny; (void)nx;
   NBH_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -69,13 +69,13 @@ struct SqBoxGeom {
   int contiguous;       // 1: a stage is ONE copy of B consecutive full rows (n_panels == 1)
   int seg_pitch;        // floats per staged row segment (segmented staging), multiple of 4
   int stage_floats;     // floats per stage (data rows, then the mask rows for M2D)
-  int mask_off;         // float offset of the mask rows inside a stage
+  int mask_off;         // float offset of the mask rows (uint8, as in mask2d) inside a stage
+  int mask_pitch;       // bytes per staged mask row segment (segmented staging), multiple of 16
   long long rows_total; // n_units * n_panels * ny
   long long share;
   int fx_shift;
   unsigned wait_ns;
   BoxStats* stats;      // [n_units]
-  const float* maskf;   // (ny, nx) float 0 / 1 plane of mask2d (M2D)
 };
 
 __device__ __forceinline__ int box_float_key(float f) {
@@ -105,10 +105,32 @@ __device__ __forceinline__ void box_wait(unsigned bar, unsigned parity, unsigned
   else mbar_wait(bar, parity);
 }
 
+// tv * 2^s -> unsigned, round to nearest even exactly like cvt.rni, without the conversion unit
+// (which the output side and the reciprocals keep busy): for 0 <= tv * 2^s <= 2^22, adding
+// 1.5 * 2^23 leaves the rounded integer in the low mantissa bits (one FFMA, one integer subtract).
+__device__ __forceinline__ unsigned box_to_fixed(float tv, float fx_scale) {
+  return __float_as_uint(__fmaf_rn(tv, fx_scale, 12582912.0f)) - 0x4B400000u;
+}
+
 // K consecutive values of a lane (K = 4 or 8): 8-byte shared loads, 16-byte ring accesses
 template <int K> __device__ __forceinline__ void box_lds(unsigned addr, float* v) {
   lds_f4(addr, v);
   if (K == 8) lds_f4(addr + 16u, v + 4);
+}
+// K mask bytes of a lane from a staged uint8 mask row, as 0 / 1 floats.  The byte address has any
+// alignment (rows of an odd multiple of two bytes), the same for every lane of the warp: aligned
+// words and a funnel shift.
+template <int K> __device__ __forceinline__ void box_lds_mask(unsigned addr, float* mk) {
+  const unsigned a4 = addr & ~3u, sh = (addr & 3u) * 8u;
+  unsigned w[K / 4 + 1];
+#pragma unroll
+  for (int c = 0; c <= K / 4; ++c) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[c]) : "r"(a4 + 4u * c));
+#pragma unroll
+  for (int c = 0; c < K / 4; ++c) {
+    const unsigned v = __funnelshift_r(w[c], w[c + 1], sh);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) mk[4 * c + b] = (v & (0xffu << (8 * b))) ? 1.f : 0.f;
+  }
 }
 template <int K> __device__ __forceinline__ void box_ring_ld(unsigned ra, unsigned* o) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(ra) : "memory");
@@ -163,7 +185,7 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
   __syncthreads();      // the only block-level barrier
 
   const unsigned long long in_elem0 = reinterpret_cast<unsigned long long>(p.in) >> 2;
-  const unsigned long long mk_elem0 = M2D ? (reinterpret_cast<unsigned long long>(g.maskf) >> 2) : 0ull;
+  const unsigned long long mk_byte0 = M2D ? reinterpret_cast<unsigned long long>(p.mask2d) : 0ull;
   const int NBP = g.n_windows_total;
 
   // ======================= producer warps =======================
@@ -188,11 +210,11 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
       const int seg0 = max(gw0 * USEFUL - HL * K, 0);
       const int seg1 = min(p.nx, gw1 * USEFUL - HL * K + kBoxWinCols);
       const float* plane_ptr = p.in + plane * p.plane_stride + seg0;
-      const float* mask_ptr = M2D ? g.maskf + seg0 : nullptr;
+      const uint8_t* mask_ptr = M2D ? p.mask2d + seg0 : nullptr;
       for (int k = 0; k < n_in; k += B) {
         const int n = min(B, n_in - k);
         const int y0 = y_lo + k;
-        box_wait(empty0 + 8 * s, (round & 1u) ^ 1u, g.wait_ns);
+        mbar_wait_backoff(empty0 + 8 * s, (round & 1u) ^ 1u, 200u);
         const unsigned dst0 = stage0 + (unsigned)s * stage_bytes;
         if (g.contiguous) {
           // one copy of n full rows (+ one for the mask rows); the producers take the stages in turn
@@ -201,11 +223,11 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
             const unsigned sh = (unsigned)(reinterpret_cast<unsigned long long>(row) & 15ull);
             const unsigned bytes = (sh + (unsigned)(n * p.nx) * 4u + 15u) & ~15u;
             unsigned total = bytes, mbytes = 0, msh = 0;
-            const float* mrow = nullptr;
+            const uint8_t* mrow = nullptr;
             if (M2D) {
               mrow = mask_ptr + (long long)y0 * p.nx;
               msh = (unsigned)(reinterpret_cast<unsigned long long>(mrow) & 15ull);
-              mbytes = (msh + (unsigned)(n * p.nx) * 4u + 15u) & ~15u;
+              mbytes = (msh + (unsigned)(n * p.nx) + 15u) & ~15u;
               total += mbytes;
             }
             mbar_expect_tx(full0 + 8 * s, total);
@@ -223,9 +245,9 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
             const unsigned sh = (unsigned)(reinterpret_cast<unsigned long long>(row) & 15ull);
             total += (sh + (unsigned)(seg1 - seg0) * 4u + 15u) & ~15u;
             if (M2D) {
-              const float* mrow = mask_ptr + (long long)(y0 + j) * p.nx;
+              const uint8_t* mrow = mask_ptr + (long long)(y0 + j) * p.nx;
               const unsigned msh = (unsigned)(reinterpret_cast<unsigned long long>(mrow) & 15ull);
-              total += (msh + (unsigned)(seg1 - seg0) * 4u + 15u) & ~15u;
+              total += (msh + (unsigned)(seg1 - seg0) + 15u) & ~15u;
             }
           }
           if (total) mbar_expect_tx(full0 + 8 * s, total); else mbar_arrive(full0 + 8 * s);
@@ -236,10 +258,10 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
             bulk_g2s(dst0 + (unsigned)(j * g.seg_pitch) * 4u, reinterpret_cast<const char*>(row) - sh, bytes,
                      full0 + 8 * s);
             if (M2D) {
-              const float* mrow = mask_ptr + (long long)(y0 + j) * p.nx;
+              const uint8_t* mrow = mask_ptr + (long long)(y0 + j) * p.nx;
               const unsigned msh = (unsigned)(reinterpret_cast<unsigned long long>(mrow) & 15ull);
-              const unsigned mbytes = (msh + (unsigned)(seg1 - seg0) * 4u + 15u) & ~15u;
-              bulk_g2s(dst0 + (unsigned)(g.mask_off + j * g.seg_pitch) * 4u,
+              const unsigned mbytes = (msh + (unsigned)(seg1 - seg0) + 15u) & ~15u;
+              bulk_g2s(dst0 + (unsigned)g.mask_off * 4u + (unsigned)(j * g.mask_pitch),
                        reinterpret_cast<const char*>(mrow) - msh, mbytes, full0 + 8 * s);
             }
           }
@@ -258,6 +280,9 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
   const float fx_scale = (float)(1u << g.fx_shift);
   const unsigned ONE = 1u << g.fx_shift;
   const float fx_inv = 1.0f / fx_scale;
+  const float nf_full = ((float)NB * fx_scale) * (float)NB;    // divisor of a window wholly inside the domain
+  float rc_full;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc_full) : "f"(nf_full));
   const unsigned stages_u32 = smem_u32(stages);
   const float kInf = __int_as_float(0x7f800000);
   float nanacc = 0.f;
@@ -299,6 +324,18 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
     const unsigned long long plane_elem0 = in_elem0 + (unsigned long long)(plane * p.plane_stride) + (unsigned long long)seg0;
     const unsigned lane_col_b = (unsigned)(x_ld - seg0) * 4u;
     const bool lane_interior = lane_full && (x0 - R >= 0) && (x0 + K - 1 + R <= p.nx - 1);
+    const bool fast_rows_ok = !sum_only && (M2D || p.out_mask == nullptr);   // (an unmasked launch that wants a mask plane takes the general path)
+    const bool warp_inner = __all_sync(0xffffffffu, lane_interior);
+    float* const out_x0 = p.out + obase0 + x0;
+    // divisors (and reciprocals) of the lane's columns for windows with all 2r+1 rows inside the domain
+    float nf_col[K], rc_col[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const int xo = x0 + i;
+      const int cols_in = max(min(xo + R, p.nx - 1) - max(xo - R, 0) + 1, 1);
+      nf_col[i] = ((float)NB * fx_scale) * (float)cols_in;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc_col[i]) : "f"(nf_col[i]));
+    }
 
     // zero the ring (rows above the domain are zeros)
 #pragma unroll
@@ -318,6 +355,202 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
     int consumed = 0;
     int k = max(0, -y_first);                               // leading rows above the domain are zeros
     while (k < n_rows) {
+      // ---- interior rows (most of the work): a run of batches whose rows are all data rows away
+      // from the top / bottom bands, so the row count of every window is 2r+1 and the divisors are
+      // per-lane constants of the piece.  The run is one tight loop that touches nothing of the
+      // piece bookkeeping (spilled state reloaded from local memory once per batch was the
+      // largest stall of the kernel, ncu r2u).  INNER: every column of the warp has its whole
+      // window inside the domain (one scalar divisor, no per-point conditions); otherwise the
+      // window touches the left or right edge: columns outside the domain are zeroed, the
+      // divisors follow the column count and the column bands of the trimming fix-up are watched.
+      if (fast_rows_ok && k >= 2 * R) {
+        const int yy_run = y_first + k;
+        const int last_start = p.ny - 1 - R - B;              // last row a fast batch may start at
+        int nfast = 0;
+        if (yy_run >= 2 * R && yy_run <= last_start)
+          nfast = min((last_start - yy_run) / B + 1, (n_in_piece - consumed) / B);
+        if (nfast > 0) {
+          auto fast_run = [&](auto inner_tag) {
+            constexpr bool INNER = decltype(inner_tag)::value;
+            unsigned a0 = (unsigned)((plane_elem0 + (unsigned long long)((long long)yy_run * p.nx)) & 3ull);
+            float* op = out_x0 + (long long)(yy_run - R) * p.nx;
+            const long long pt_run = (long long)(yy_run - R) * p.nx + x0;   // first output point of the lane
+            const float* cp = M2D ? p.cnt_plane + pt_run : nullptr;
+            const uint8_t* mp = (M2D && p.out_mask) ? p.mask2d + pt_run : nullptr;
+            uint8_t* omp = (M2D && p.out_mask) ? p.out_mask + obase0 + pt_run : nullptr;
+            unsigned am0 = M2D ? (unsigned)((mk_byte0 + (unsigned long long)((long long)yy_run * p.nx + seg0)) & 15ull) : 0u;
+            const unsigned lane_col = (unsigned)(x_ld - seg0), mpitch = (unsigned)g.mask_pitch;
+            const unsigned nxu = (unsigned)p.nx, pitch = (unsigned)g.seg_pitch;
+            const bool contiguous = g.contiguous != 0;
+            for (int it = 0; it < nfast; ++it) {
+              float d[B][K];
+              float mk[M2D ? B : 1][K];
+              float cnt[M2D ? B : 1][K];
+              if (M2D) {
+                // the counts of the output rows: requested before the wait, used at the very end
+#pragma unroll
+                for (int j = 0; j < B; ++j) {
+                  if (out_lane && (INNER || lane_full)) {
+#pragma unroll
+                    for (int i = 0; i < K; i += 2) {
+                      const float2 c2 = __ldg(reinterpret_cast<const float2*>(cp + j * p.nx + i));
+                      cnt[j][i] = c2.x; cnt[j][i + 1] = c2.y;
+                    }
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+                      cnt[j][i] = (out_lane && ((okbits >> i) & 1u)) ? __ldg(cp + j * p.nx + i) : 1.f;
+                  }
+                }
+              }
+              mbar_wait(bar, parity);
+#pragma unroll
+              for (int j = 0; j < B; ++j) {
+                const unsigned e = a0 + (unsigned)j * nxu;
+                const unsigned off = contiguous ? e : ((e & 3u) + (unsigned)j * pitch);
+                box_lds<K>(st_addr + off * 4u + lane_col_b, &d[j][0]);
+                if (M2D) {
+                  const unsigned em = am0 + (unsigned)j * nxu;
+                  const unsigned moff = contiguous ? em : ((em & 15u) + (unsigned)j * mpitch);
+                  box_lds_mask<K>(st_addr + (unsigned)g.mask_off * 4u + moff + lane_col, &mk[j][0]);
+                }
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar + 8 * kBoxMaxStages);
+              bar += 8; st_addr += stage_bytes;
+              if (++s == NS) { s = 0; parity ^= 1u; bar = full0; st_addr = stages_u32; }
+              a0 = (a0 + (unsigned)B * nxu) & 3u;
+              if (M2D) am0 = (am0 + (unsigned)B * nxu) & 15u;
+              if (INNER || lane_full) {
+#pragma unroll
+                for (int j = 0; j < B; ++j) { dmax = box_max_nan<K>(d[j], dmax); dmin = box_min<K>(d[j], dmin); }
+              } else if (okbits) {
+#pragma unroll
+                for (int j = 0; j < B; ++j)
+#pragma unroll
+                  for (int i = 0; i < K; ++i)
+                    if ((okbits >> i) & 1u) { dmax = max_nan(dmax, d[j][i]); dmin = fminf(dmin, d[j][i]); }
+              }
+              unsigned q[B][K];
+#pragma unroll
+              for (int j = 0; j < B; ++j)
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                  float tv = truth_value_sum<TM>(d[j][i], thr);
+                  if (M2D) tv *= mk[j][i];
+                  q[j][i] = box_to_fixed(tv, fx_scale);
+                  if (!INNER) q[j][i] = ((okbits >> i) & 1u) ? q[j][i] : 0u;
+                }
+              if (!INNER) {
+                if ((band_l && !(ne_bits & 4u)) || (band_r && !(ne_bits & 8u))) {
+#pragma unroll
+                  for (int j = 0; j < B; ++j)
+#pragma unroll
+                    for (int i = 0; i < K; ++i) {
+                      const int xo = x0 + i;
+                      if (((okbits >> i) & 1u) && q[j][i] != ONE) {
+                        if (xo <= R) ne_bits |= 4u;
+                        if (xo >= p.nx - 1 - R) ne_bits |= 8u;
+                      }
+                    }
+                }
+              }
+              unsigned Vs[B][K];
+              if (NB >= B) {
+                unsigned o[B][K];
+                unsigned ra[B];
+#pragma unroll
+                for (int j = 0; j < B; ++j) {
+                  ra[j] = ring_u32 + (unsigned)slot * (kBoxWinCols * 4u);
+                  slot = (slot + 1 == NB) ? 0 : slot + 1;
+                }
+#pragma unroll
+                for (int j = 0; j < B; ++j) box_ring_ld<K>(ra[j], o[j]);
+#pragma unroll
+                for (int j = 0; j < B; ++j) {
+                  box_ring_st<K>(ra[j], q[j]);
+#pragma unroll
+                  for (int i = 0; i < K; ++i) { V[i] += q[j][i] - o[j][i]; Vs[j][i] = V[i]; }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < B; ++j) {
+                  const unsigned ra = ring_u32 + (unsigned)slot * (kBoxWinCols * 4u);
+                  unsigned o[K];
+                  box_ring_ld<K>(ra, o);
+                  box_ring_st<K>(ra, q[j]);
+#pragma unroll
+                  for (int i = 0; i < K; ++i) { V[i] += q[j][i] - o[i]; Vs[j][i] = V[i]; }
+                  slot = (slot + 1 == NB) ? 0 : slot + 1;
+                }
+              }
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+              unsigned E[K + 2 * R];
+#pragma unroll
+              for (int i = 0; i < R; ++i) {
+                const int ol = R - i, dl = (ol + K - 1) / K;
+                const int orr = i + 1, dr = (orr + K - 1) / K;
+                E[i] = __shfl_up_sync(0xffffffffu, Vs[j][dl * K - ol], dl);
+                E[K + R + i] = __shfl_down_sync(0xffffffffu, Vs[j][i - (dr - 1) * K], dr);
+              }
+#pragma unroll
+              for (int i = 0; i < K; ++i) E[R + i] = Vs[j][i];
+              unsigned part[3] = {0u, 0u, 0u};
+#pragma unroll
+              for (int c = 0; c <= 2 * R; ++c) part[c % 3] += E[c];
+              unsigned H[K];
+              H[0] = part[0] + part[1] + part[2];
+#pragma unroll
+              for (int i = 1; i < K; ++i) H[i] = H[i - 1] + E[i + 2 * R] - E[i - 1];
+              float o[K];
+#pragma unroll
+              for (int i = 0; i < K; ++i) {
+                float nf, rc;
+                if (M2D) {
+                  nf = cnt[j][i] * fx_scale;
+                  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(nf));
+                } else {
+                  nf = INNER ? nf_full : nf_col[i];
+                  rc = INNER ? rc_full : rc_col[i];
+                }
+                const float Sf = (float)H[i];
+                const float q0 = Sf * rc;
+                const float rem = __fmaf_rn(-q0, nf, Sf);
+                o[i] = __fmaf_rn(rem, rc, q0);
+                if (M2D) o[i] = cnt[j][i] == 0.f ? __int_as_float(0x7fc00000) : o[i];
+              }
+              if (out_lane) {
+                if (INNER || lane_full) {
+                  omax = box_max<K>(o, omax);
+                  omin = box_min<K>(o, omin);
+#pragma unroll
+                  for (int i = 0; i < K; i += 2) *reinterpret_cast<float2*>(op + i) = make_float2(o[i], o[i + 1]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < K; ++i)
+                    if ((okbits >> i) & 1u) { omax = fmaxf(omax, o[i]); omin = fminf(omin, o[i]); op[i] = o[i]; }
+                }
+                if (omp) {
+#pragma unroll
+                  for (int i = 0; i < K; ++i)
+                    if ((okbits >> i) & 1u) omp[i] = (M2D && mp[i] == 0) ? 1 : 0;
+                }
+              }
+              op += p.nx;
+              if (M2D) { cp += p.nx; if (mp) mp += p.nx; }
+              if (omp) omp += p.nx;
+            }
+            }
+          };
+          if (warp_inner) fast_run(std::true_type{});
+          else fast_run(std::false_type{});
+          k += nfast * B;
+          consumed += nfast * B;
+          continue;
+        }
+      }
+
       const int yy0 = y_first + k;
       const bool has_data = yy0 < p.ny;
       int nbr;
@@ -327,7 +560,7 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
         nbr = min(B, n_in_piece - consumed);
         box_wait(bar, parity, g.wait_ns);
         const unsigned long long e0 = plane_elem0 + (unsigned long long)((long long)yy0 * p.nx);
-        const unsigned long long m0 = M2D ? mk_elem0 + (unsigned long long)((long long)yy0 * p.nx + seg0) : 0ull;
+        const unsigned long long m0 = M2D ? mk_byte0 + (unsigned long long)((long long)yy0 * p.nx + seg0) : 0ull;
 #pragma unroll
         for (int j = 0; j < B; ++j) {
           // rows past the end of the piece re-read the first row of the stage (ignored later)
@@ -335,13 +568,13 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
           unsigned off, moff = 0;
           if (g.contiguous) {
             off = (unsigned)(e0 & 3ull) * 4u + (unsigned)(jj * p.nx) * 4u;
-            if (M2D) moff = (unsigned)(m0 & 3ull) * 4u + (unsigned)(jj * p.nx) * 4u;
+            if (M2D) moff = (unsigned)(m0 & 15ull) + (unsigned)(jj * p.nx);
           } else {
             off = (unsigned)((e0 + (unsigned long long)(jj * p.nx)) & 3ull) * 4u + (unsigned)(jj * g.seg_pitch) * 4u;
-            if (M2D) moff = (unsigned)((m0 + (unsigned long long)(jj * p.nx)) & 3ull) * 4u + (unsigned)(jj * g.seg_pitch) * 4u;
+            if (M2D) moff = (unsigned)((m0 + (unsigned long long)(jj * p.nx)) & 15ull) + (unsigned)(jj * g.mask_pitch);
           }
           box_lds<K>(st_addr + off + lane_col_b, &d[j][0]);
-          if (M2D) box_lds<K>(st_addr + (unsigned)g.mask_off * 4u + moff + lane_col_b, &mk[j][0]);
+          if (M2D) box_lds_mask<K>(st_addr + (unsigned)g.mask_off * 4u + moff + (lane_col_b >> 2), &mk[j][0]);
         }
         consumed += nbr;
         __syncwarp();                                       // every lane has read the stage
@@ -398,11 +631,7 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
           for (int i = 0; i < K; ++i) {
             float tv = truth_value_sum<TM>(d[j][i], thr);
             if (M2D) tv *= mk[j][i];
-#ifdef NBH_BOX_FAKE_CVT
-            q[j][i] = __float_as_uint(tv * fx_scale);      // timing experiment only: no conversion unit
-#else
-            q[j][i] = __float2uint_rn(tv * fx_scale);
-#endif
+            q[j][i] = box_to_fixed(tv, fx_scale);
           }
         }
         if (warp_edge || !has_data) {
@@ -534,11 +763,7 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
                   nf = nrow * (float)(min(xo + R, p.nx - 1) - max(xo - R, 0) + 1);
                   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(nf));
                 }
-#ifdef NBH_BOX_FAKE_CVT
-                const float Sf = __uint_as_float(H[i]);
-#else
                 const float Sf = (float)H[i];
-#endif
                 const float q0 = Sf * rc;
                 const float rem = __fmaf_rn(-q0, nf, Sf);
                 o[i] = __fmaf_rn(rem, rc, q0);
@@ -608,7 +833,6 @@ struct BoxWorkspace {
   float2* range;
   int* n_clamp;
   int* n_redo;
-  float* maskf;
 };
 size_t box_workspace_bytes(long long n_units, int ny, int nx);
 void box_carve(void* ws, long long n_units, int ny, int nx, BoxWorkspace* w);

@@ -147,6 +147,7 @@ square_mt_kernel(const __grid_constant__ SqParams p, const SqMtGeom g) {
 #pragma unroll
     for (int i = 0; i < K; ++i) okbits |= (win_active && x0 + i >= 0 && x0 + i < p.nx) ? (1u << i) : 0u;
     const bool lane_full = okbits == FULLBITS;
+    const bool lane_whole = lane_full || okbits == 0;        // all four loaded values are data (a lane without columns reads the first group)
     const bool warp_edge = __any_sync(0xffffffffu, !lane_full);
     const int x_ld = okbits ? x0 : seg0;
     const bool out_lane = lane >= HL && lane < 32 - HL && okbits != 0;
@@ -184,7 +185,14 @@ square_mt_kernel(const __grid_constant__ SqParams p, const SqMtGeom g) {
             float d[K];
             lds_f4(a, d);
             a += pitch_b;
-            if (check_nan) { nanacc = max3_nan(nanacc, d[0], d[1]); nanacc = max3_nan(nanacc, d[2], d[3]); }
+            if (check_nan) {
+              // a partial lane (row end) reads whatever follows the row in the stage: only its valid columns count
+              if (lane_whole) { nanacc = max3_nan(nanacc, d[0], d[1]); nanacc = max3_nan(nanacc, d[2], d[3]); }
+              else {
+#pragma unroll
+                for (int i = 0; i < K; ++i) if ((okbits >> i) & 1u) nanacc = max_nan(nanacc, d[i]);
+              }
+            }
 #pragma unroll
             for (int i = 0; i < K; ++i) acc[i] += truth_value_sum<TM>(d[i], thr);
           }
