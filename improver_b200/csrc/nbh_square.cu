@@ -537,7 +537,6 @@ int run_square(const NbhDesc* d, const float* in, float* out, uint8_t* out_mask,
     BoxWorkspace bw;
     box_carve(w.box, nslices, d->ny, d->nx, &bw);
     if (box_prepare(bw, nullptr, nslices, d->ny, d->nx, st)) return 1;
-    if (!sum_only && launch_edge_flags(p, tm, st)) return 1;
     {
       ProfileScope prof(st, "nbh::square_v_kernel + nbh::square_h_kernel (two-pass fixed point, L2-resident intermediate)");
       rc = launch_square_vh(p, *d, tm_warp, vh_shift, bw.stats, w.vh, st);

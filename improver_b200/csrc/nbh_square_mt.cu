@@ -125,19 +125,19 @@ edge_flags_kernel(const SqParams p) {
   for (int t = 0; t < kMaxThresholds; ++t) bits[t] = 0u;
   const int band = min(r + 1, ny), bandx = min(r + 1, nx);
   // rows of the top and bottom bands (all columns), then the left / right column bands of every row
-  const long long n_rowpts = 2LL * band * nx, n_colpts = 2LL * bandx * ny;
+  // (32-bit point arithmetic: the bands of a slice hold far fewer than 2^31 points, checked by the launcher)
+  const unsigned n_rowpts = 2u * (unsigned)band * (unsigned)nx, n_colpts = 2u * (unsigned)bandx * (unsigned)ny;
   // blockIdx.y: one of gridDim.y interleaved parts of the band points of the slice
-  for (long long i = (long long)blockIdx.y * blockDim.x + threadIdx.x; i < n_rowpts + n_colpts;
-       i += (long long)gridDim.y * blockDim.x) {
+  for (unsigned i = blockIdx.y * blockDim.x + threadIdx.x; i < n_rowpts + n_colpts; i += gridDim.y * blockDim.x) {
     int y, x;
     if (i < n_rowpts) {
-      const int k = (int)(i / nx);
-      x = (int)(i - (long long)k * nx);
+      const int k = (int)(i / (unsigned)nx);
+      x = (int)(i - (unsigned)k * (unsigned)nx);
       y = k < band ? k : ny - band + (k - band);
     } else {
-      const long long j = i - n_rowpts;
-      y = (int)(j / (2 * bandx));
-      const int k = (int)(j - (long long)y * 2 * bandx);
+      const unsigned j = i - n_rowpts;
+      y = (int)(j / (2u * (unsigned)bandx));
+      const int k = (int)(j - (unsigned)y * 2u * (unsigned)bandx);
       x = k < bandx ? k : nx - bandx + (k - bandx);
     }
     const long long pt = (long long)y * nx + x;
@@ -162,7 +162,8 @@ int launch_edge_flags(const SqParams& p, int tm, cudaStream_t st) {
   const long long n = p.n_planes * p.n_members;
   NBH_REQUIRE(n < (1LL << 31), "too many slices");
   const long long pts = 2LL * (p.r + 1) * ((long long)p.nx + p.ny);
-  const unsigned parts = (unsigned)max(1LL, min(16LL, pts / 4096));
+  NBH_REQUIRE(pts < (1LL << 31), "edge bands too large");
+  const unsigned parts = (unsigned)max(1LL, min(32LL, pts / 2048));
   edge_flags_kernel<<<dim3((unsigned)n, parts), 256, 0, st>>>(p);
   NBH_CHECK_CUDA(cudaGetLastError());
   return 0;

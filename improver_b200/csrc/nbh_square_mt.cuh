@@ -100,7 +100,7 @@ square_mt_kernel(const __grid_constant__ SqParams p, const SqMtGeom g) {
         const unsigned bytes = (shift_b + (unsigned)(seg1 - seg0) * 4u + 15u) & ~15u;
         const char* src = reinterpret_cast<const char*>(row) - shift_b;
         for (int m0 = 0; m0 < Rm; m0 += MS) {
-          mbar_wait(empty0 + 8 * s, (round & 1u) ^ 1u);
+          mbar_wait_backoff(empty0 + 8 * s, (round & 1u) ^ 1u, 200u);    // stages of slack: no polling against the math warps
           if (n_mine) mbar_expect_tx(full0 + 8 * s, bytes * (unsigned)n_mine); else mbar_arrive(full0 + 8 * s);
           unsigned dst = stage0 + (unsigned)s * stage_bytes + (unsigned)(pw * g.pitch) * 4u;
           const char* q = src + (long long)(m0 + pw) * p.member_stride * 4;
@@ -126,7 +126,8 @@ square_mt_kernel(const __grid_constant__ SqParams p, const SqMtGeom g) {
   const unsigned stages_u32 = smem_u32(stages);
   const unsigned pitch_b = (unsigned)g.pitch * 4u;
   const bool check_nan = tl == 0;                           // the warps of one window see the same data
-  float nanacc = 0.f;
+  float nan_lo = 0.f, nan_hi = 0.f;
+  bool nan_seen = false;
   int s = 0;
   unsigned parity = 0, bar = full0, st_addr = stages_u32;
 
@@ -177,30 +178,31 @@ square_mt_kernel(const __grid_constant__ SqParams p, const SqMtGeom g) {
       for (int i = 0; i < K; ++i) acc[i] = 0.f;
       if (in_dom) {
         const unsigned shift_b = (unsigned)((plane_elem0 + (unsigned long long)((long long)yy * p.nx)) & 3ull) * 4u;
-        for (int m0 = 0; m0 < Rm; m0 += MS) {
-          mbar_wait(bar, parity);
-          unsigned a = st_addr + lane_col_b + shift_b;
-#pragma unroll 3
-          for (int j = 0; j < MS; ++j) {
-            float d[K];
-            lds_f4(a, d);
-            a += pitch_b;
-            if (check_nan) {
-              // a partial lane (row end) reads whatever follows the row in the stage: only its valid columns count
-              if (lane_whole) { nanacc = max3_nan(nanacc, d[0], d[1]); nanacc = max3_nan(nanacc, d[2], d[3]); }
-              else {
+        // the member loop, specialised on the NaN watch (one threshold's warps carry it for their window)
+        auto members = [&](auto watch_tag) {
+          constexpr bool WATCH = decltype(watch_tag)::value;
+          for (int m0 = 0; m0 < Rm; m0 += MS) {
+            mbar_wait(bar, parity);
+            unsigned a = st_addr + lane_col_b + shift_b;
+#pragma unroll 6
+            for (int j = 0; j < MS; ++j) {
+              float d[K];
+              lds_f4(a, d);
+              a += pitch_b;
+              // the two column pairs apart: a partial lane (row end, nx is even: exactly its first pair
+              // is valid) reads whatever follows the row in the stage in its second pair
+              if (WATCH) { nan_lo = max3_nan(nan_lo, d[0], d[1]); nan_hi = max3_nan(nan_hi, d[2], d[3]); }
 #pragma unroll
-                for (int i = 0; i < K; ++i) if ((okbits >> i) & 1u) nanacc = max_nan(nanacc, d[i]);
-              }
+              for (int i = 0; i < K; ++i) acc[i] += truth_value_sum<TM>(d[i], thr);
             }
-#pragma unroll
-            for (int i = 0; i < K; ++i) acc[i] += truth_value_sum<TM>(d[i], thr);
+            __syncwarp();                                   // every lane has read the stage
+            if (lane == 0) mbar_arrive(bar + 8 * kMtMaxStages);
+            bar += 8; st_addr += stage_bytes;
+            if (++s == NS) { s = 0; parity ^= 1u; bar = full0; st_addr = stages_u32; }
           }
-          __syncwarp();                                   // every lane has read the stage
-          if (lane == 0) mbar_arrive(bar + 8 * kMtMaxStages);
-          bar += 8; st_addr += stage_bytes;
-          if (++s == NS) { s = 0; parity ^= 1u; bar = full0; st_addr = stages_u32; }
-        }
+        };
+        if (check_nan) members(std::true_type{});
+        else members(std::false_type{});
         if (M2D) {
           // the external mask is shared by all members: one multiply per column and row
 #pragma unroll
@@ -285,8 +287,10 @@ square_mt_kernel(const __grid_constant__ SqParams p, const SqMtGeom g) {
         }
       }
     }
+    nan_seen = nan_seen || __isnanf(nan_lo) || (lane_whole && __isnanf(nan_hi));
+    nan_lo = nan_hi = 0.f;
   }
-  if (__any_sync(0xffffffffu, __isnanf(nanacc))) {
+  if (__any_sync(0xffffffffu, nan_seen)) {
     if (lane == 0) atomicOr(reinterpret_cast<unsigned*>(p.status), 1u);
   }
 }

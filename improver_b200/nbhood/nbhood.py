@@ -229,9 +229,9 @@ class NeighbourhoodProcessing(BaseNeighbourhoodProcessing):
         masked_in = isinstance(data, np.ma.MaskedArray)
         arr = np.ma.transpose(data, perm) if masked_in else np.transpose(data, perm)
         result = self._calculate_neighbourhood(arr, mask_cube_data)
-        has_mask_source = masked_in or mask_cube_data is not None
         if isinstance(result, np.ma.MaskedArray):
-            result = np.ma.transpose(result, inv) if has_mask_source else np.transpose(result.data, inv)
+            # re_mask: a MaskedArray even without any mask source (all-False mask, nbhood.py:314-317)
+            result = np.ma.transpose(result, inv)
         else:
             result = np.transpose(result, inv)
         return cube.copy(data=result)

@@ -140,6 +140,20 @@ def test_process_probability_cube_vs_oracle(method):
     assert plugin.nb_size == 11
 
 
+def test_process_re_mask_without_mask_source_is_masked_array():
+    """nbhood.py:314-317: re_mask wraps the result in a MaskedArray even when nothing is masked."""
+    rng = np.random.default_rng(5)
+    data = rng.random((2, 30, 36)).astype(np.float32)
+    cube = set_up_probability_cube(data, [1.0, 2.0])
+    for re_mask in (True, False):
+        res = NeighbourhoodProcessing("square", 6000, re_mask=re_mask)(cube).data
+        assert isinstance(res, np.ma.MaskedArray) == re_mask
+        if re_mask:
+            assert not np.ma.getmaskarray(res).any()
+        exp, _ = orc.neighbourhood_cube(data, None, method="square", cells=3)
+        np.testing.assert_allclose(np.ma.getdata(res), exp, atol=1e-5)
+
+
 def test_process_lead_time_radii_and_mask_cube():
     """nbhood.py:132-175: radius interpolated at the cube's forecast period;
     land-sea style mask cube with re_mask (config 2 semantics)."""
