@@ -187,7 +187,13 @@ def neighbourhood_sharded(data: torch.Tensor, cells: int, gather: bool = False, 
     world = _world(group)
     rank = _rank(group)
     s0, s1 = shard_range(data.shape[0], world, rank)
-    out, omask, status = engine.neighbourhood(data[s0:s1].contiguous(), cells, **kwargs)
+    if s1 > s0:
+        out, omask, status = engine.neighbourhood(data[s0:s1].contiguous(), cells, **kwargs)
+    else:
+        # more ranks than slices: this rank has no share; one slice gives the trailing shape
+        out, omask, status = engine.neighbourhood(data[:1].contiguous(), cells, **kwargs)
+        out = out[:0]
+        omask = None if omask is None else omask[:0]
     if not gather:
         return out, omask, status, (s0, s1)
     sizes = [shard_range(data.shape[0], world, r) for r in range(world)]

@@ -38,6 +38,7 @@ def multi_rank_parity(device, ny: int = 192, nx: int = 256, n_slices: int = 6, s
     result of this rank's band, for square (plain, masked, periodic x), circular, the
     ones-trimming quirk case and sharded percentiles.  Max over ranks."""
     world, rank = dist.get_world_size(), dist.get_rank()
+    n_slices = max(n_slices, world + 1)                   # every rank a share, the shares uneven
     full = workloads.counter_uniform(0, n_slices, (ny, nx), seed, device)
     g = torch.Generator(device="cpu").manual_seed(seed)
     mask = (torch.rand((ny, nx), generator=g) < 0.8).to(torch.uint8).to(device)
