@@ -32,6 +32,13 @@ bad = [k for k in ("sharded_max_abs", "tiled_max_abs", "tiled_quirk_case", "perc
        if res[k] != 0.0]
 if res["tiled_quirk_fixed_slices"] < 2:
     bad.append("quirk case did not trigger the fix-up")
+# fewer slices than ranks: a rank without a share still takes part in the gather
+from improver_b200 import distributed as D, engine, workloads
+one = workloads.counter_uniform(0, 1, (40, 64), 3, dev)
+ref, _, st = engine.neighbourhood(one, 3)
+got, _, st, (s0, s1) = D.neighbourhood_sharded(one, 3, gather=True)
+if not torch.equal(got, ref) or (rank == 1 and s1 != s0):
+    bad.append("empty share")
 if rank == 0:
     print(json.dumps(res))
     print("MULTI_GPU_OK" if not bad else f"MULTI_GPU_FAIL {bad}")
