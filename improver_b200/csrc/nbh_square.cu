@@ -365,7 +365,17 @@ static void carve_workspace(const NbhDesc& d, void* ws, SqWorkspace* w) {
   w->box = base + off;
   if (d.n_members == 1) off = align_up(off + box_workspace_bytes((long long)nslices, d.ny, d.nx), 256);
   w->vh = reinterpret_cast<unsigned*>(base + off);
-  if (d.n_members == 1 && d.cells > 8 && d.cells <= 63) off = align_up(off + vh_workspace_bytes(d), 256);
+  // the intermediate plane of the two-pass kernels: needed exactly when they may run, i.e. the launch
+  // has their shape but not the box kernel's (both ask for the same pointer alignment, so a shape the
+  // box kernel takes never reaches them); decided by the planners themselves on an aligned stand-in
+  {
+    const float* aligned = reinterpret_cast<const float*>(static_cast<uintptr_t>(256));
+    SqBoxGeom bg;
+    int grid = 0, shift = 0;
+    size_t smem = 0;
+    if (!plan_square_box(d, aligned, &bg, &grid, &smem) && plan_square_vh(d, aligned, &shift))
+      off = align_up(off + vh_workspace_bytes(d), 256);
+  }
   w->total = off;
 }
 

@@ -214,6 +214,7 @@ square_h_kernel(const VhParams p, int row_pitch) {
   const int r = p.r, nx = p.nx, nb = 2 * r + 1;
   const int n_cols_padded = (nx + 127) / 128 * 128;          // the prefix step works on whole 128-column groups
   const bool sum_only = (p.flags & NBH_SUM_ONLY) != 0;
+  const bool wrap_x = (p.flags & NBH_WRAP_X) != 0;
   const float scale = (float)(1u << p.fx_shift), inv_scale = 1.0f / scale;
   const long long n_rows = (long long)p.n_units_chunk * p.ny;
   float omin = __int_as_float(0x7f800000), omax = __int_as_float(0xff800000);
@@ -317,11 +318,22 @@ square_h_kernel(const VhParams p, int row_pitch) {
       // the columns whose window is cut by the row ends (all of them in a row narrower than two windows)
       auto cut_column = [&](int xo) {
         const int hi = min(xo + r, nx - 1), lo = xo - r - 1;
-        const unsigned S = P[hi] - (lo >= 0 ? P[lo] : 0u);
+        unsigned S;
+        int cols_in;
+        if (wrap_x) {
+          // periodic x (global grids): the part of the window beyond a row end comes from the other end
+          const unsigned total = P[nx - 1];
+          if (xo + r >= nx) S = total + P[xo + r - nx] - P[lo];
+          else S = P[xo + r] + total - P[nx + lo];          // (lo == -1: nothing wraps, total - P[nx - 1] = 0)
+          cols_in = nb;
+        } else {
+          S = P[hi] - (lo >= 0 ? P[lo] : 0u);
+          cols_in = hi - max(xo - r, 0) + 1;
+        }
         float nf = 1.f, rc = 1.f;
         if (!SUM) {
           if (M2D) nf = __ldg(p.cnt_plane + (long long)y * nx + xo) * scale;
-          else nf = nrow * (float)(hi - max(xo - r, 0) + 1);
+          else nf = nrow * (float)cols_in;
           asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(nf));
         }
         finish(xo, S, nf, rc);
@@ -352,7 +364,8 @@ square_h_kernel(const VhParams p, int row_pitch) {
 bool plan_square_vh(const NbhDesc& d, const float* in, int* fx_shift) {
   const int r = d.cells, nb = 2 * r + 1;
   if (d.n_members != 1 || r < 1 || r > 63) return false;
-  if ((d.flags & NBH_WRAP_X) || d.mask_nd) return false;
+  if (d.mask_nd) return false;
+  if ((d.flags & NBH_WRAP_X) && d.nx < 2 * r + 2) return false;     // a window wraps at one row end at most
   if ((d.nx & 1) || d.nx < 2 || (reinterpret_cast<uintptr_t>(in) & 7) || (d.plane_stride & 1)) return false;
   if ((size_t)(d.nx + 132) * 4 * 2 * kVhHWarps > 200u * 1024) return false;
   int shift = 0;
