@@ -79,7 +79,6 @@ bool plan_square_box(const NbhDesc& d, const float* in, SqBoxGeom* g, int* grid,
   int shift = 0;
   while (shift < 22 && (double)nb * nb * (double)(1u << (shift + 1)) < 4294967296.0) ++shift;   // <= 22: box_to_fixed
   g->fx_shift = shift;
-  g->wait_ns = 0;
   g->rows_total = d.n_planes * (long long)max(d.n_thresholds, 1) * n_panels * d.ny;
   const int per_sm = budget < (size_t)smem_max ? 2 : 1;
   const long long min_share = max(32, 8 * r);

@@ -2,29 +2,34 @@
 // improver/nbhood/nbhood.py:244-317 + boxsum, improver/utilities/neighbourhood_tools.py:129-211):
 // row-streaming box kernel with register-resident horizontal windows.
 //
-// One persistent block per SM slot owns a contiguous share of the (slice, y) rows.  Producer
-// threads stream batches of B rows into a ring of shared-memory stages with bulk asynchronous
-// copies (cp.async.bulk / mbarrier, as square_rs_kernel); every consumer warp owns a window of
-// 256 columns, EIGHT consecutive columns per lane, and marches down the rows:
+// One persistent block per SM slot (two per SM) owns a contiguous share of the (slice, y) rows.  A
+// producer thread streams batches of B rows into a ring of shared-memory stages with bulk
+// asynchronous copies (cp.async.bulk / mbarrier, as square_rs_kernel); every consumer warp owns a
+// window of 128 columns, FOUR consecutive columns per lane, and marches down the rows:
 //
 //   vertical window  : the (thresholded, masked) values are turned into exact fixed point
 //                      (q = v * 2^s, round to nearest) and each lane keeps the running column
-//                      sums V += q_new - q_old of its eight columns in registers; the last 2r+1
+//                      sums V += q_new - q_old of its four columns in registers; the last 2r+1
 //                      quantised rows live in a warp-private shared-memory ring (16-byte
 //                      accesses, conflict free);
 //   horizontal window: compile-time radius R <= 8: a lane needs the column sums of columns
-//                      x0-R .. x0+7+R, i.e. its own eight, the last R of its left neighbour and
-//                      the first R of its right neighbour: 2R warp shuffles, then one 2R+1-term
-//                      sum and seven sliding updates (IADD3) — no scan, no prefix row, no
-//                      barrier.  Lane 0 and lane 31 of a window are halo lanes (240 useful
-//                      columns per window);
+//                      x0-R .. x0+3+R, i.e. its own four and R on either side from the one or
+//                      two neighbouring lanes: 2R warp shuffles, then one 2R+1-term sum and three
+//                      sliding updates (IADD3) — no scan, no prefix row, no barrier.  ceil(R/4)
+//                      lanes at either end of a window are halo lanes (112 useful columns per
+//                      window for R = 5);
 //   normalise        : S / (rows_in * cols_in) as a correctly rounded float32 quotient
 //                      (reciprocal + two FMAs), or S / count[y][x] for an external mask.
 //
-// Unsigned 32-bit arithmetic throughout: (2r+1)^2 * 2^s < 2^32, so window sums are exact for the
-// quantised values whatever row a share or a y-band starts at (bit-identical bands), a window of
-// ones gives exactly 1 and a window of zeros exactly 0.  The quantisation contributes at most
-// 2^-(s+1) (3e-8 for r = 5) to a mean.  Raw slices are processed on the assumption that they are
+// The rows of a piece away from the top / bottom bands run in a tight loop of their own (fast_run)
+// that touches none of the piece bookkeeping: the kernel is capped at 80 registers, the bookkeeping
+// spills, and spill reloads inside the per-batch loop miss the (almost absent) L1 and were the
+// dominant stall.
+//
+// Unsigned 32-bit arithmetic throughout: (2r+1)^2 * 2^s < 2^32 (s <= 22), so window sums are exact
+// for the quantised values whatever row a share or a y-band starts at (bit-identical bands), a
+// window of ones gives exactly 1 and a window of zeros exactly 0.  The quantisation contributes at
+// most 2^-(s+1) (1e-7) to a mean.  Raw slices are processed on the assumption that they are
 // probabilities in [0, 1]; the kernel records the extremes of every slice and of its results, and
 // the host queues (device-side guarded) follow-ups: slices outside [0, 1] are recomputed by the
 // float64 kernels, slices whose results left [min, max] by the quantisation are clamped
@@ -38,10 +43,7 @@ namespace nbh {
 
 constexpr int kBoxProducers = 1;         // one thread issues a bulk copy every ~500 cycles: a stage of B rows
                                          // per 500 cycles is several times what the consumers can take
-#ifndef NBH_BOX_K
-#define NBH_BOX_K 4
-#endif
-constexpr int kBoxK = NBH_BOX_K;             // consecutive columns per lane (4 or 8)
+constexpr int kBoxK = 4;                     // consecutive columns per lane (8 was measured: same time raw, slower masked)
 constexpr int kBoxWinCols = 32 * kBoxK;      // columns a warp loads
 constexpr int kBoxMaxWindows = kBoxK == 8 ? 6 : 10;   // consumer warps per block
 constexpr int kBoxThreads = (kBoxMaxWindows + kBoxProducers) * 32;
@@ -49,10 +51,7 @@ constexpr int kBoxThreads = (kBoxMaxWindows + kBoxProducers) * 32;
 __host__ __device__ constexpr int box_halo_lanes(int r) { return (r + kBoxK - 1) / kBoxK; }
 __host__ __device__ constexpr int box_useful_cols(int r) { return (32 - 2 * box_halo_lanes(r)) * kBoxK; }
 constexpr int kBoxMaxStages = 8;
-#ifndef NBH_BOX_BPLAIN
-#define NBH_BOX_BPLAIN 2
-#endif
-constexpr int kBoxBPlain = NBH_BOX_BPLAIN, kBoxBMasked = 2;   // rows per stage / batch (masked launches stage a mask row per data row)
+constexpr int kBoxBPlain = 2, kBoxBMasked = 2;   // rows per stage / batch (four rows spill registers)
 
 // per-slice extremes recorded by the box kernel (ordered-int keys, see float_key)
 struct BoxStats {
@@ -74,7 +73,6 @@ struct SqBoxGeom {
   long long rows_total; // n_units * n_panels * ny
   long long share;
   int fx_shift;
-  unsigned wait_ns;
   BoxStats* stats;      // [n_units]
 };
 
@@ -96,14 +94,10 @@ __device__ __forceinline__ void lds_f4(unsigned addr, float* v) {
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+8];" : "=f"(v[2]), "=f"(v[3]) : "r"(addr));
 }
 
-// barrier wait: plain try_wait loop (the hardware blocks the thread for a short, bounded time per
-// try); a suspend-time hint turns every miss into a ~1 us sleep, which with a handful of stages
-// in flight serialises the producer / consumer hand-over (ncu r2c: half of the executed
-// instructions were SYNCS / NANOSLEEP / BRA of those loops, DRAM at 26 %)
-__device__ __forceinline__ void box_wait(unsigned bar, unsigned parity, unsigned hint_ns) {
-  if (hint_ns) mbar_wait_hint(bar, parity, hint_ns);
-  else mbar_wait(bar, parity);
-}
+// Barrier waits of the consumers are plain try_wait loops (the hardware blocks the thread for a
+// short, bounded time per try): a suspend-time hint turned every miss into a ~1 us sleep, which with
+// a handful of stages in flight serialised the producer / consumer hand-over (ncu r2c).  The producer
+// thread, which has stages of slack, sleeps between tries (mbar_wait_backoff).
 
 // tv * 2^s -> unsigned, round to nearest even exactly like cvt.rni, without the conversion unit
 // (which the output side and the reciprocals keep busy): for 0 <= tv * 2^s <= 2^22, adding
@@ -558,7 +552,7 @@ square_box_kernel(const __grid_constant__ SqParams p, const SqBoxGeom g) {
       float mk[M2D ? B : 1][K];
       if (has_data) {
         nbr = min(B, n_in_piece - consumed);
-        box_wait(bar, parity, g.wait_ns);
+        mbar_wait(bar, parity);
         const unsigned long long e0 = plane_elem0 + (unsigned long long)((long long)yy0 * p.nx);
         const unsigned long long m0 = M2D ? mk_byte0 + (unsigned long long)((long long)yy0 * p.nx + seg0) : 0ull;
 #pragma unroll
