@@ -524,6 +524,152 @@ circ_gather_tiled_kernel(const CircGlobalParams p, const __grid_constant__ CircW
   }
 }
 
+// Same staging, four outputs per thread: a warp covers 128 consecutive columns of a tile row, lane l
+// the columns x0 + l + 32 j (j = 0..3), so the width lookup, the two span addresses and the row step
+// of a kernel row are shared by four results and every shared-memory read of a warp is 32 consecutive
+// words (no bank conflict): 2 loads + 3 integer operations per result and kernel row instead of ~10
+// instructions.  Land / sea launches stage one plane at a time (a pass is skipped for tiles without
+// points of its type), so all four results of a thread read the same tile.
+constexpr int kCircTW4 = 128;
+
+template <typename PT, bool LS, bool PW, bool BOTH>
+__global__ void __launch_bounds__(256)
+circ_gather_tiled4_kernel(const CircGlobalParams p, const __grid_constant__ CircWidths cw, int TH, int tiles_x,
+                          int tiles_y) {
+  if (p.guarded && *p.guard == 0) return;
+  typedef typename CircAcc<PT>::acc_t acc_t;
+  extern __shared__ __align__(16) unsigned char smem_c[];
+  const int r = p.r;
+  const int TC = kCircTW4 + 2 * r + 1, TR = TH + 2 * r;
+  PT* tile = reinterpret_cast<PT*>(smem_c);            // [TR][TC], col j <-> global col x0 - r - 1 + j
+
+  long long bid = blockIdx.x;
+  const int tx = (int)(bid % tiles_x); bid /= tiles_x;
+  const int ty = (int)(bid % tiles_y); bid /= tiles_y;
+  const int b = (int)bid;
+  const int x0 = tx * kCircTW4, y0 = ty * TH;
+  const long long per_plane = (long long)p.ny * p.nx;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const long long plane = p.plane0 + b;
+  const int cshift = r + 1 - x0;                                // tile column of global column gc: gc + cshift
+  const bool wrap = (p.flags & NBH_WRAP_X) != 0;
+  int xj[4];
+  bool fast[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    xj[j] = x0 + lane + 32 * j;
+    // every span of the column inside the row (or periodic x); columns past the row end never store
+    const bool inner = wrap || (xj[j] - r - 1 >= -1 && xj[j] + r <= p.nx - 1);
+    fast[j] = __all_sync(0xffffffffu, xj[j] >= p.nx || inner) != 0;
+  }
+  const bool fast_all = fast[0] && fast[1] && fast[2] && fast[3];
+  // land / sea: both planes staged side by side when they fit (BOTH: one compute pass, every result
+  // reads the plane of its own type), else one plane at a time
+  constexpr bool SEQ = LS && !BOTH;
+  const size_t plane_cells = (size_t)TR * TC;
+#pragma unroll 1
+  for (int k = 0; k < (LS ? 2 : 1); ++k) {
+    PT* tl = tile + ((LS && BOTH && k == 1) ? plane_cells : 0);
+    if (SEQ) {
+      bool mine = false;
+      for (int ly = warp; ly < TH; ly += n_warps) {
+        const int y = y0 + ly;
+        if (y >= p.ny) break;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (xj[j] < p.nx) mine = mine || ((p.mask2d[(long long)y * p.nx + xj[j]] == 0) == (k == 1));
+      }
+      if (!__syncthreads_or(mine ? 1 : 0)) continue;
+    }
+    const PT* pre = reinterpret_cast<const PT*>(k ? p.prefix2 : p.prefix) + (long long)b * per_plane;
+    // stage: a warp per tile row, lanes along the row (no index division, coalesced)
+    for (int jr = warp; jr < TR; jr += n_warps) {
+      const int ys = min(max(y0 - r + jr, 0), p.ny - 1);          // edge replication in y
+      const PT* src = pre + (long long)ys * p.nx;
+      PT* dst = tl + (size_t)jr * TC;
+#pragma unroll 2
+      for (int jc = lane; jc < TC; jc += 32) {
+        const int gc = x0 - r - 1 + jc;
+        if (wrap) dst[jc] = wrap_prefix<PT>(src, gc, p.nx);
+        else dst[jc] = gc < 0 ? (PT)0 : src[min(gc, p.nx - 1)];
+      }
+    }
+    if (LS && BOTH && k == 0) continue;                       // stage the sea plane too, then one compute pass
+    __syncthreads();
+    for (int ly = warp; ly < TH; ly += n_warps) {
+      const int y = y0 + ly;
+      if (y >= p.ny) break;
+      bool want[4];
+      int poff[4];                                            // element offset of the plane a result reads
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        want[j] = xj[j] < p.nx;
+        poff[j] = 0;
+        if (LS && want[j]) {
+          const bool sea = p.mask2d[(long long)y * p.nx + xj[j]] == 0;
+          if (SEQ) want[j] = sea == (k == 1);
+          else poff[j] = sea ? (int)plane_cells : 0;
+        }
+      }
+      // sequential land / sea passes: a stretch of 128 columns without a point of this pass's type is skipped
+      if (SEQ && !__any_sync(0xffffffffu, want[0] || want[1] || want[2] || want[3])) continue;
+      acc_t S[4] = {0, 0, 0, 0};
+      if (fast_all) {
+        const PT* rowp = tile + (size_t)ly * TC + cshift + x0 + lane;   // column x0 + lane of the first kernel row
+#pragma unroll 2
+        for (int dy = 0; dy <= 2 * r; ++dy) {
+          const int w = PW ? (int)cw.w[dy] : p.wtab[dy < r ? r - dy : dy - r];
+          const PT* hi = rowp + w;
+          const PT* lo = rowp - w - 1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) S[j] += (acc_t)(PT)(hi[32 * j + poff[j]] - lo[32 * j + poff[j]]);
+          rowp += TC;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int x = xj[j];
+          if (x >= p.nx) continue;
+          if (fast[j]) {
+            const PT* rowp = tile + (size_t)ly * TC + cshift + x + poff[j];
+#pragma unroll 4
+            for (int dy = 0; dy <= 2 * r; ++dy) {
+              const int w = PW ? (int)cw.w[dy] : p.wtab[dy < r ? r - dy : dy - r];
+              S[j] += (acc_t)(PT)(rowp[w] - rowp[-w - 1]);
+              rowp += TC;
+            }
+          } else {
+            for (int dy = -r; dy <= r; ++dy) {
+              const int w = PW ? (int)cw.w[dy + r] : p.wtab[dy < 0 ? -dy : dy];
+              const PT* row = tile + (size_t)(ly + r + dy) * TC + cshift + poff[j];   // indexable by global column >= -1
+              const int lo = max(x - w, 0), hi = min(x + w, p.nx - 1);
+              PT s2 = row[hi] - row[lo - 1];
+              const int nl = lo - (x - w), nr = (x + w) - hi;             // replicated edge cells (mode="nearest")
+              if (nl > 0) s2 += (PT)nl * (row[0] - row[-1]);
+              if (nr > 0) s2 += (PT)nr * (row[p.nx - 1] - row[p.nx - 2]);
+              S[j] += (acc_t)s2;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (want[j]) circ_store<PT>(p, S[j], 0.0, false, plane, (long long)y * p.nx + xj[j], per_plane);
+    }
+    if (SEQ) __syncthreads();                                  // the buffer is restaged for the other plane
+  }
+}
+
+static int circ_tile4_rows(int r, int nx, size_t elem, int n_planes, size_t* smem) {
+  if (nx < 3) return 0;
+  for (int th : {64, 32, 16}) {
+    const size_t cells = (size_t)(th + 2 * r) * (kCircTW4 + 2 * r + 1);
+    const size_t bytes = (size_t)n_planes * cells * elem;
+    if (bytes <= 72u * 1024 && cells <= (size_t)12 * th * kCircTW4) { *smem = bytes; return th; }
+  }
+  return 0;
+}
+
 // pick the tallest tile that fits; 0 = use the direct gather.  Measured on B200: tiles pay while
 // several blocks fit on an SM and the staged window is well reused (a 200 KB tile per SM at r = 81
 // was 1.7 x SLOWER than the direct gather from L1 / L2).  n_tiles = 2: both land / sea planes at once.
@@ -543,6 +689,27 @@ static int launch_circ_gather_t(const CircGlobalParams& g, const CircWidths& cw,
   size_t smem = 0;
   int th = 0;
   bool both = false;
+  if (!g.cprefix && allow_tile) {
+    // land / sea: both planes side by side while a tile of at least 32 rows fits, else sequential passes
+    int th4 = LS ? circ_tile4_rows(g.r, nx, sizeof(PT), 2, &smem) : 0;
+    const bool both4 = th4 >= 32;
+    if (!both4) th4 = circ_tile4_rows(g.r, nx, sizeof(PT), 1, &smem);
+    if (th4 > 0) {
+      const int tiles_x = (nx + kCircTW4 - 1) / kCircTW4, tiles_y = (ny + th4 - 1) / th4;
+      const long long blocks = (long long)tiles_x * tiles_y * g.n_batch;
+      NBH_REQUIRE(blocks < (1LL << 31), "too many blocks");
+      if (both4) {
+        auto kern = circ_gather_tiled4_kernel<PT, LS, PW, true>;
+        NBH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)blocks, 256, smem, st>>>(g, cw, th4, tiles_x, tiles_y);
+      } else {
+        auto kern = circ_gather_tiled4_kernel<PT, LS, PW, false>;
+        NBH_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)blocks, 256, smem, st>>>(g, cw, th4, tiles_x, tiles_y);
+      }
+      return 0;
+    }
+  }
   if (!g.cprefix && allow_tile) {
     if (LS) {
       // both planes side by side while a tall tile fits; else one buffer, the planes one after the other
