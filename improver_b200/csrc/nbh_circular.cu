@@ -436,6 +436,82 @@ circ_gather_kernel(const CircGlobalParams p, const __grid_constant__ CircWidths 
   circ_store<PT>(p, S, A, cpre != nullptr, p.plane0 + b, pt, per_plane);
 }
 
+// Direct gather, four results per thread and eight rows per block: a warp covers 128 consecutive
+// columns of one output row (lane l the columns x0 + l + 32 j), the eight warps of a block eight
+// consecutive rows, so the (8 + 2r) x (128 + 2r + 1) prefix values a block touches are shared by its
+// 1024 results through L1 instead of every 256-point block streaming its own 2(2r+1) rows from L2
+// (the one-point-per-thread kernel moved ~8 B per result and kernel row through L2: 6.8 TB/s at
+// r = 81, the L2 bound).  Not for periodic x or count prefixes (circ_gather_kernel).
+template <typename PT, bool LS, bool PW>
+__global__ void __launch_bounds__(256)
+circ_gather4_kernel(const CircGlobalParams p, const __grid_constant__ CircWidths cw, int tiles_x, int tiles_y) {
+  if (p.guarded && *p.guard == 0) return;
+  typedef typename CircAcc<PT>::acc_t acc_t;
+  long long bid = blockIdx.x;
+  const int tx = (int)(bid % tiles_x); bid /= tiles_x;
+  const int ty = (int)(bid % tiles_y); bid /= tiles_y;
+  const int b = (int)bid;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x0 = tx * 128, y = ty * 8 + warp;
+  if (y >= p.ny) return;
+  const int r = p.r;
+  const long long per_plane = (long long)p.ny * p.nx;
+  const PT* pre = reinterpret_cast<const PT*>(p.prefix) + (long long)b * per_plane;
+  const PT* pre2 = LS ? reinterpret_cast<const PT*>(p.prefix2) + (long long)b * per_plane : nullptr;
+  int xj[4];
+  bool want[4], fast[4];
+  const PT* base[4];                                              // the plane of the result's own type, at its column
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    xj[j] = x0 + lane + 32 * j;
+    want[j] = xj[j] < p.nx;
+    const bool inner = xj[j] - r - 1 >= 0 && xj[j] + r <= p.nx - 1;
+    fast[j] = __all_sync(0xffffffffu, !want[j] || inner) != 0;
+    // (columns past the row end read a column whose spans lie inside the row; never stored)
+    const int xc = want[j] ? xj[j] : max(min(xj[j], p.nx - 1 - r), min(r + 1, p.nx - 1));
+    const bool sea = LS && p.mask2d[(long long)y * p.nx + xc] == 0;
+    base[j] = (sea ? pre2 : pre) + xc;
+  }
+  acc_t S[4] = {0, 0, 0, 0};
+  if (fast[0] && fast[1] && fast[2] && fast[3] && x0 + 127 + r <= p.nx - 1 && x0 - r - 1 >= 0) {
+    // every span of every column inside the row: per kernel row one row offset and one width for four results
+#pragma unroll 2
+    for (int dy = -r; dy <= r; ++dy) {
+      const int w = PW ? (int)cw.w[dy + r] : p.wtab[dy < 0 ? -dy : dy];
+      const long long ro = (long long)min(max(y + dy, 0), p.ny - 1) * p.nx;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const PT* q = base[j] + ro;
+        S[j] += (acc_t)(PT)(q[w] - q[-w - 1]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!__any_sync(0xffffffffu, want[j])) continue;
+      if (fast[j]) {
+#pragma unroll 4
+        for (int dy = -r; dy <= r; ++dy) {
+          const int w = PW ? (int)cw.w[dy + r] : p.wtab[dy < 0 ? -dy : dy];
+          const PT* q = base[j] + (long long)min(max(y + dy, 0), p.ny - 1) * p.nx;
+          S[j] += (acc_t)(PT)(q[w] - q[-w - 1]);
+        }
+        continue;
+      }
+      if (!want[j]) continue;
+      const PT* pl = base[j] - xj[j];                             // start of the plane of the result's type (want: base is at xj)
+      for (int dy = -r; dy <= r; ++dy) {
+        const int w = PW ? (int)cw.w[dy + r] : p.wtab[dy < 0 ? -dy : dy];
+        const int ys = min(max(y + dy, 0), p.ny - 1);
+        S[j] += (acc_t)span_sum<PT>(pl + (long long)ys * p.nx, xj[j], w, p.nx);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (want[j]) circ_store<PT>(p, S[j], 0.0, false, p.plane0 + b, (long long)y * p.nx + xj[j], per_plane);
+}
+
 // Shared-memory tiled gather: a block stages the (TH + 2r) x (TW + 2r + 1) window of prefix
 // values its TH x TW outputs need (each value is then read ~2(2r+1) times from shared memory
 // instead of L1 / L2); LAND_SEA stages the window of both planes.
@@ -691,9 +767,13 @@ static int launch_circ_gather_t(const CircGlobalParams& g, const CircWidths& cw,
   bool both = false;
   if (!g.cprefix && allow_tile) {
     // land / sea: both planes side by side while a tile of at least 32 rows fits, else sequential passes
-    int th4 = LS ? circ_tile4_rows(g.r, nx, sizeof(PT), 2, &smem) : 0;
+    // land / sea launches gather directly (circ_gather4_kernel) whenever that kernel applies: measured
+    // on 240 UK slices against the tiles with both planes side by side (r = 5: 4.9 / 5.2 ms, r = 9:
+    // 6.2 / 7.0 ms) and against staging the planes one after the other (r = 27: 12.5 / 16.5 ms)
+    const bool ls_direct = LS && nx >= 128 && !(g.flags & NBH_WRAP_X);
+    int th4 = (LS && !ls_direct) ? circ_tile4_rows(g.r, nx, sizeof(PT), 2, &smem) : 0;
     const bool both4 = th4 >= 32;
-    if (!both4) th4 = circ_tile4_rows(g.r, nx, sizeof(PT), 1, &smem);
+    if (!both4) th4 = ls_direct ? 0 : circ_tile4_rows(g.r, nx, sizeof(PT), 1, &smem);
     if (th4 > 0) {
       const int tiles_x = (nx + kCircTW4 - 1) / kCircTW4, tiles_y = (ny + th4 - 1) / th4;
       const long long blocks = (long long)tiles_x * tiles_y * g.n_batch;
@@ -710,7 +790,7 @@ static int launch_circ_gather_t(const CircGlobalParams& g, const CircWidths& cw,
       return 0;
     }
   }
-  if (!g.cprefix && allow_tile) {
+  if (!g.cprefix && allow_tile && !(LS && nx >= 128 && !(g.flags & NBH_WRAP_X))) {
     if (LS) {
       // both planes side by side while a tall tile fits; else one buffer, the planes one after the other
       th = circ_tile_rows(g.r, nx, sizeof(PT), 2, &smem);
@@ -733,8 +813,15 @@ static int launch_circ_gather_t(const CircGlobalParams& g, const CircWidths& cw,
       kern<<<(unsigned)blocks, 256, smem, st>>>(g, cw, th, tiles_x, tiles_y);
     }
   } else {
-    const long long outs = (long long)g.n_batch * ny * nx;
-    circ_gather_kernel<PT, LS, PW><<<(unsigned)((outs + 255) / 256), 256, 0, st>>>(g, cw);
+    if (!g.cprefix && !(g.flags & NBH_WRAP_X) && nx >= 128) {
+      const int tiles_x = (nx + 127) / 128, tiles_y = (ny + 7) / 8;
+      const long long blocks = (long long)tiles_x * tiles_y * g.n_batch;
+      NBH_REQUIRE(blocks < (1LL << 31), "too many blocks");
+      circ_gather4_kernel<PT, LS, PW><<<(unsigned)blocks, 256, 0, st>>>(g, cw, tiles_x, tiles_y);
+    } else {
+      const long long outs = (long long)g.n_batch * ny * nx;
+      circ_gather_kernel<PT, LS, PW><<<(unsigned)((outs + 255) / 256), 256, 0, st>>>(g, cw);
+    }
   }
   return 0;
 }
