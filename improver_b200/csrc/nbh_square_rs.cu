@@ -31,8 +31,11 @@ bool plan_square_rs(const NbhDesc& d, const float* in, SqRsGeom* g, int* grid) {
   const size_t fixed = sq_rs_fixed_smem(nb, n_windows) + 256;
   if (fixed + 2 * (size_t)pitch * 4 > (size_t)smem_max) return false;
   const size_t avail = (size_t)smem_max - fixed;
-  // items per stage: the largest divisor of R whose stage stays below ~1/5 of the ring
-  const size_t stage_cap = max((size_t)pitch * 4, min((size_t)32 * 1024, avail / 5));
+  // items per stage: the largest divisor of R that leaves room for three stages.  Every stage costs a
+  // consumer warp ~60 instructions of hand-over (barrier wait, arrive, stage pointer), and the kernel
+  // runs at 80 % of its issue slots: with 18 members, 6 rows per stage (the ~25 KB stages of round 1)
+  // took 0.49 ms per cube, 9 rows 0.46 ms, 18 rows (two stages) 0.456 ms, 3 rows 0.60 ms
+  const size_t stage_cap = max((size_t)pitch * 4, avail / 3);
   int ms = 1;
   for (int c = 1; c <= R; ++c)
     if (R % c == 0 && (size_t)c * pitch * 4 <= stage_cap) ms = c;
