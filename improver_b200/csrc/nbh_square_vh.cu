@@ -1,24 +1,27 @@
 // Square neighbourhood of single-member slices for radii beyond the box kernel's shuffle window
-// (9 .. 63 cells): two radius-independent passes over exact fixed-point values.
+// (9 .. 63 cells) and for a periodic x axis at every radius: two radius-independent passes over
+// exact fixed-point values.
 //
 //   V pass  (square_v_kernel): a thread owns two adjacent columns of a y segment and marches down
 //           the rows keeping the vertical window sum of the quantised (thresholded, masked) values,
-//           V += q(y + r) - q(y - r - 1).  The entering row comes straight from global memory
-//           (coalesced across the block, eight rows in flight per thread), the leaving value from a
-//           shared-memory ring of the 2r + 1 quantised rows of the window (8 bytes per thread and
-//           row, every thread its own column: no barrier).  V is written to an intermediate uint32
-//           plane.
-//   H pass  (square_h_kernel): a warp owns a row of the intermediate plane: staged in shared
-//           memory, turned into its inclusive prefix in place (four consecutive values per lane and
+//           V += q(y + r) - q(y - r - 1).  The entering rows come straight from global memory
+//           (coalesced across the block; sixteen rows per batch, the next batch requested before
+//           the current one is consumed), the leaving value from a shared-memory ring of the 2r + 1
+//           quantised rows of the window (8 bytes per thread and row, every thread its own column:
+//           no barrier).  It also records the slice extremes and the edge-band flags of the
+//           trimming fix-up.  V is written to an intermediate uint32 plane.
+//   H pass  (square_h_kernel): a warp owns a row of the intermediate plane: copied to shared
+//           memory with cp.async (the next row in flight while the current one is worked on),
+//           turned into its inclusive prefix in place (four consecutive values per lane and
 //           128-column step: lane scan, warp scan of the totals, 16-byte accesses), every result is
-//           the difference of two prefix values, normalised like the box kernel (correctly rounded
-//           quotient) and stored coalesced.
+//           the difference of two prefix values (three for the columns of a periodic row whose
+//           window wraps), normalised like the box kernel (correctly rounded quotient) and stored
+//           coalesced.
 //
 // The intermediate plane (4 B / point) goes through HBM: chunks small enough to keep it in L2
-// (<= 64 MB = 16 UK slices) were measured and lose more to the small grids (192 blocks per V launch,
-// latency-bound) than they save in traffic (2.2 ms against the numbers in DESIGN.md for 240 slices);
-// the launch is only cut when the plane would exceed 1 GB.  DRAM traffic ~ 20 B / point (input read,
-// leaving rows mostly from L2, intermediate written and read, output written).  Cost does not
+// (<= 64 MB = 16 UK slices) were measured and lose more to the small grids than they save in
+// traffic; the launch is only cut when the plane would exceed 1 GB.  DRAM traffic ~ 17 B / point
+// (input read incl. 5 % halo rows, intermediate written and read, output written).  Cost does not
 // depend on the radius.  Same arithmetic contract as square_box_kernel: unsigned 32-bit sums with
 // (2r+1)^2 * 2^s < 2^32, band-origin independent, slice extremes recorded for the guarded clamp /
 // float64 re-run (box_finish).
@@ -28,7 +31,7 @@ namespace nbh {
 
 constexpr int kVhSegRowsMax = 512;       // rows per y segment of the V pass (2r halo rows are re-read per segment); halved while the grid is small
 constexpr size_t kVhChunkBytes = (size_t)1 << 30;   // intermediate plane per chunk of planes (see the header comment)
-constexpr int kVhRows = 16;              // output rows per step of the V pass: 2 * kVhRows row loads in flight per thread
+constexpr int kVhRows = 16;              // rows per batch of the V pass (a batch in flight while the previous one is consumed)
 
 struct VhParams {
   const float* in;
