@@ -442,8 +442,10 @@ circ_gather_kernel(const CircGlobalParams p, const __grid_constant__ CircWidths 
 // 1024 results through L1 instead of every 256-point block streaming its own 2(2r+1) rows from L2
 // (the one-point-per-thread kernel moved ~8 B per result and kernel row through L2: 6.8 TB/s at
 // r = 81, the L2 bound).  Not for periodic x or count prefixes (circ_gather_kernel).
+constexpr int kCircG4Rows = 8;                  // rows (warps) per block of the direct four-result gather (16 was measured: 2-4 % slower at every radius)
+
 template <typename PT, bool LS, bool PW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kCircG4Rows * 32)
 circ_gather4_kernel(const CircGlobalParams p, const __grid_constant__ CircWidths cw, int tiles_x, int tiles_y) {
   if (p.guarded && *p.guard == 0) return;
   typedef typename CircAcc<PT>::acc_t acc_t;
@@ -452,7 +454,7 @@ circ_gather4_kernel(const CircGlobalParams p, const __grid_constant__ CircWidths
   const int ty = (int)(bid % tiles_y); bid /= tiles_y;
   const int b = (int)bid;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int x0 = tx * 128, y = ty * 8 + warp;
+  const int x0 = tx * 128, y = ty * kCircG4Rows + warp;
   if (y >= p.ny) return;
   const int r = p.r;
   const long long per_plane = (long long)p.ny * p.nx;
@@ -814,10 +816,10 @@ static int launch_circ_gather_t(const CircGlobalParams& g, const CircWidths& cw,
     }
   } else {
     if (!g.cprefix && !(g.flags & NBH_WRAP_X) && nx >= 128) {
-      const int tiles_x = (nx + 127) / 128, tiles_y = (ny + 7) / 8;
+      const int tiles_x = (nx + 127) / 128, tiles_y = (ny + kCircG4Rows - 1) / kCircG4Rows;
       const long long blocks = (long long)tiles_x * tiles_y * g.n_batch;
       NBH_REQUIRE(blocks < (1LL << 31), "too many blocks");
-      circ_gather4_kernel<PT, LS, PW><<<(unsigned)blocks, 256, 0, st>>>(g, cw, tiles_x, tiles_y);
+      circ_gather4_kernel<PT, LS, PW><<<(unsigned)blocks, kCircG4Rows * 32, 0, st>>>(g, cw, tiles_x, tiles_y);
     } else {
       const long long outs = (long long)g.n_batch * ny * nx;
       circ_gather_kernel<PT, LS, PW><<<(unsigned)((outs + 255) / 256), 256, 0, st>>>(g, cw);
