@@ -56,3 +56,40 @@ def test_shard_range_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         D.shard_range(4, 2, 2)
+
+
+def _sharded_worker(rank, world, port, n_slices, results):
+    """neighbourhood_sharded with a stand-in for the native call (a 3-point mean along x on the CPU):
+    the host logic under test is the share of every rank, the rank without a share when there are
+    more ranks than slices, and the gather of uneven shares."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from improver_b200 import engine
+
+        def fake_neighbourhood(data, cells, **kwargs):
+            assert data.shape[0] >= 1, "the native entry point rejects empty input"
+            pad = torch.nn.functional.pad(data, (1, 1), mode="replicate")
+            out = (pad[..., :-2] + pad[..., 1:-1] + pad[..., 2:]) / 3
+            return out, None, torch.zeros(2, dtype=torch.int32)
+
+        engine.neighbourhood = fake_neighbourhood
+        full = torch.arange(n_slices * 5 * 6, dtype=torch.float32).reshape(n_slices, 5, 6)
+        ref, _, _ = fake_neighbourhood(full, 1)
+        got, _, _, (s0, s1) = D.neighbourhood_sharded(full, 1, gather=True)
+        ok = torch.equal(got, ref) and (s0, s1) == D.shard_range(n_slices, world, rank)
+        part, _, _, _ = D.neighbourhood_sharded(full, 1, gather=False)
+        ok = ok and torch.equal(part, ref[s0:s1])
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_slices", [(2, 5), (3, 2), (3, 1)])
+def test_sharded_neighbourhood_uneven_and_empty_shares(world, n_slices):
+    port = _free_port()
+    with mp.Manager() as mgr:
+        results = mgr.dict()
+        mp.spawn(_sharded_worker, args=(world, port, n_slices, results), nprocs=world, join=True)
+        assert dict(results) == {r: True for r in range(world)}
